@@ -1,0 +1,132 @@
+/*
+ * morfem_b200 -- C ABI of the B200 (sm_100a) reduced-order frequency-sweep path.
+ *
+ * The reference (SzymonKnopp/morfem) has no FFI layer: its boundary is the Python function API of
+ * implementation.py / test_helpers.py.  Each entry point below replaces the third-party CPU call that the
+ * reference reaches at the cited line; morfem_b200/implementation.py keeps the reference's Python signatures
+ * and calls these through ctypes (see INTEGRATION.md for the binding a reference maintainer would add).
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers unless the name ends in _host; complex128 is interleaved (re, im);
+ *   - dense matrices are row-major with an explicit leading dimension in elements;
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*; NULL = default stream);
+ *   - return value: 0 ok, <0 = -(index of the offending argument, 1-based), >0 = cudaError_t of a failed
+ *     launch / API call; mf_last_error() returns a thread-local description;
+ *   - no call allocates or frees device memory: workspaces are sized by the *_ws_bytes queries and owned by
+ *     the caller; nothing here synchronises the device.
+ */
+#ifndef MORFEM_B200_H
+#define MORFEM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct { double re, im; } mf_c128;
+
+#define MF_VERSION 100
+#define MF_MAX_PORTS 16
+
+int mf_version(void);
+const char* mf_last_error(void);
+/* Number of kernels launched by this library in the calling process so far (bench.py "gpu_launches"). */
+int64_t mf_launch_count(void);
+
+/* ---- stage 1 + 2 dense contractions ------------------------------------------------------------------
+ * C (ra x rb) = op(A)^T B summed over n rows; A is n x ra, B is n x rb; conj_a != 0 selects A^H (Gram /
+ * north-star Q^H), 0 selects the plain transpose of implementation.py:180 (`q_t = q.T`).
+ * Replaces BLAS dgemm behind `(q_t @ a) @ q` (implementation.py:181-183) and the Gram products of the
+ * CholeskyQR2 replacement of np.linalg.svd (implementation.py:226, :298, :210).
+ * Split over row ranges; partials go to `ws` and are summed in a fixed order (deterministic). */
+size_t mf_gemm_tn_ws_bytes(int ra, int rb, int64_t n);
+int mf_gemm_tn_c128(const mf_c128* A, int64_t lda, int ra, const mf_c128* B, int64_t ldb, int rb, int64_t n,
+                    int conj_a, mf_c128* C, int64_t ldc, void* ws, size_t ws_bytes, void* stream);
+
+/* Out (n x rb) = A (n x ra) * W (ra x rb).  The `S R^-1` / `Q1 (R2^-1 U)` applications of CholeskyQR2 and
+ * the lift Q x.  Out must not alias A. */
+int mf_gemm_nn_c128(const mf_c128* A, int64_t lda, int64_t n, int ra, const mf_c128* W, int64_t ldw, int rb,
+                    mf_c128* Out, int64_t ldo, void* stream);
+
+/* ---- r x r factorisations used by the basis stage (all single-launch, device-resident) ---------------
+ * mf_equilibrate:   d[j] = 1/sqrt(real(G[j][j])) (1 if the diagonal is not positive); G <- diag(d) G diag(d)
+ *                   + shift * I.  stats[0] = max_ij |G_ij - delta_ij| of the INPUT (departure of the block whose
+ *                   Gram matrix G is from orthonormality; the CholeskyQR pass counter tests it), stats may be NULL.
+ * mf_potrf_upper:   Cholesky G = R^H R, R upper triangular written over G (strict lower part zeroed);
+ *                   *info = 0 or the 1-based column at which a non-positive pivot appeared.
+ * mf_trtri_upper:   Rinv = R^-1 (upper triangular), Rinv must not alias R.
+ * mf_scale_cols / mf_scale_rows: X[:, j] *= d[j]^p / X[i, :] *= d[i]^p with p = +1 or -1.
+ * mf_jacobi_svd:    one-sided Jacobi SVD of the r x r matrix X: on exit U holds the left singular vectors
+ *                   (columns, sorted by descending sigma), sigma the singular values; X and work are
+ *                   destroyed.  Replaces LAPACK gesdd on the small factor (np.linalg.svd of the snapshot
+ *                   block = CholeskyQR2 + SVD of R).  Cooperative launch: needs r/2 <= co-resident CTAs. */
+int mf_equilibrate_c128(mf_c128* G, int64_t ld, int r, double shift, double* d, double* stats, void* stream);
+int mf_potrf_upper_c128(mf_c128* G, int64_t ld, int r, int* info, void* stream);
+int mf_trtri_upper_c128(const mf_c128* R, int64_t ldr, int r, mf_c128* Rinv, int64_t ldi, void* stream);
+int mf_scale_cols_c128(mf_c128* X, int64_t ld, int rows, int cols, const double* d, int power, void* stream);
+int mf_scale_rows_c128(mf_c128* X, int64_t ld, int rows, int cols, const double* d, int power, void* stream);
+size_t mf_jacobi_svd_ws_bytes(int r);
+int mf_jacobi_svd_c128(mf_c128* X, int64_t ld, int r, mf_c128* U, int64_t ldu, double* sigma, int max_sweeps,
+                       double tol, int* sweeps_done, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- stage 2 sparse ------------------------------------------------------------------------------------
+ * Y (nrows x r) = A Q with A in CSR (int32 indices; values real f64 when val_is_real != 0 else c128).
+ * The reference's `q_t @ a` (implementation.py:181-183) is scipy's csr_matvecs over the CSR view of a^T, i.e.
+ * the CSC arrays of `a` passed here unchanged give Y = a^T Q.  Row-sharded callers pass their slice of the
+ * row pointer array rebased to start at 0 together with the matching slices of colidx/vals; column indices
+ * stay global (they index rows of Q). */
+int mf_spmm_csr_c128(const int32_t* rowptr, const int32_t* colidx, const void* vals, int val_is_real,
+                     int64_t nrows, const mf_c128* Q, int64_t ldq, int r, mf_c128* Y, int64_t ldy, void* stream);
+
+/* B_r (r x m) = Q^T B (conj_q != 0: Q^H B) for B in CSC (n x m, int32 indices, real or complex values);
+ * implementation.py:184 `q_t @ md.b`.  Rows outside [row0, row0 + nlocal) are skipped so that row-sharded
+ * callers can all-reduce the partial results; Q points at the caller's first local row. */
+int mf_project_rhs_c128(const int32_t* colptr, const int32_t* rowidx, const void* vals, int val_is_real, int m,
+                        const mf_c128* Q, int64_t ldq, int r, int64_t row0, int64_t nlocal, int conj_q,
+                        mf_c128* Br, int64_t ldb, void* stream);
+
+/* As (r x r) = (A + A^T) / 2: the symmetrisation of implementation.py:528 hoisted out of the sweep loop
+ * (linear in the operators, so applying it once to each reduced operator is the same mathematics). */
+int mf_symmetrize_c128(const mf_c128* A, int64_t lda, int r, mf_c128* As, int64_t lds, void* stream);
+
+/* ---- stages 3 + 4: the batched reduced sweep -------------------------------------------------------------
+ * For every point i < F:
+ *     A_i = c0[i] A0 + c1[i] A1 + c2[i] A2          (operators already symmetrised; NULL operator = zero)
+ *     X_i = A_i^-1 (cb[i] Br)                        LU with partial pivoting (LAPACK getrf/getrs semantics,
+ *                                                    implementation.py:477-478)
+ *     Z_i = j zscale[i] X_i^T (cb[i] Br),  Y_i = Z_i^-1,  S_i = 2 (I + Y_i)^-1 - I     (test_helpers.py:9-14,
+ *                                                    zscale[i] = 2 pi f_i eps0)
+ * Outputs: S (F x m x m) when non-NULL, X (F x r x m) when non-NULL, info[i] = 0 or the 1-based column of the
+ * first exactly-zero pivot (LAPACK convention).  `variant`: 0 = auto, 1 = generic (one CTA per point),
+ * 2 = register-panel kernel (r <= 128), 3 = blocked DMMA kernel.  ws from mf_sweep_ws_bytes. */
+size_t mf_sweep_ws_bytes(int r, int m, int64_t F, int variant);
+int mf_sweep_lu_gsm_c128(const mf_c128* A0, const mf_c128* A1, const mf_c128* A2, int64_t lda,
+                         const mf_c128* Br, int64_t ldb, int r, int m,
+                         const double* c0, const double* c1, const double* c2, const double* cb,
+                         const double* zscale, int64_t F,
+                         mf_c128* X, mf_c128* S, int* info, int variant,
+                         void* ws, size_t ws_bytes, void* stream);
+
+/* Stage 4 on its own (test_helpers.py:9-14 applied to F points): S_i from given solutions X (F x r x m) and
+ * port matrix Bmat (r x m): Z_i = j zscale[i] X_i^T (cb[i] Bmat), S_i = 2 (I + Z_i^-1)^-1 - I. */
+int mf_gsm_c128(const mf_c128* X, const mf_c128* Bmat, int64_t ldb, int r, int m, const double* cb,
+                const double* zscale, int64_t F, mf_c128* S, void* stream);
+
+/* ---- "next" row N1: residual error estimator of the greedy basis search (implementation.py:348-452) --------
+ * For every point i, with x_i = X[i] (r x m) from the sweep:
+ *     E_i = sum_{a,b} c_a c_b x^H G_ab x - cb sum_a c_a x^H H_a - cb sum_a c_a H_a^H x + cb^2 BB      (m x m)
+ *     err[i] = || E_i ||_F                                                     (implementation.py:424-441)
+ * G_ab = (A_a Q)^H (A_b Q) (r x r), H_a = (A_a Q)^H B (r x m), BB = B^H B (m x m), all row-major, tightly packed.
+ * G_host is a HOST array of 9 device pointers (index 3a + b), H_host a HOST array of 3; NULL entries are zero
+ * blocks.  The reference forms the same blocks as sparse products h(a_i) @ a_j (implementation.py:370-402). */
+int mf_estimator_c128(const mf_c128* X, int r, int m, int64_t F, const mf_c128* const* G_host,
+                      const mf_c128* const* H_host, const mf_c128* BB,
+                      const double* c0, const double* c1, const double* c2, const double* cb,
+                      double* err, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MORFEM_B200_H */

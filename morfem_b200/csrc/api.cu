@@ -1,0 +1,70 @@
+// C-ABI glue: version / error reporting and the dispatcher of the batched reduced sweep.
+#include "sweep_common.cuh"
+
+thread_local char g_mf_err[512] = "";
+std::atomic<long long> g_mf_launches{0};
+
+// variant entry points (defined in sweep_*.cu)
+int sweep_generic_launch(const SweepParams& p, size_t ws_bytes, cudaStream_t stream);
+size_t sweep_generic_ws_bytes(int r, int m, long long F);
+int sweep_regpanel_launch(const SweepParams& p, cudaStream_t stream);
+bool sweep_regpanel_supports(int r, int m);
+int sweep_blocked_launch(const SweepParams& p, size_t ws_bytes, cudaStream_t stream);
+size_t sweep_blocked_ws_bytes(int r, int m, long long F);
+bool sweep_blocked_supports(int r, int m);
+
+extern "C" int mf_version(void) { return MF_VERSION; }
+extern "C" const char* mf_last_error(void) { return g_mf_err; }
+extern "C" int64_t mf_launch_count(void) { return (int64_t)g_mf_launches.load(std::memory_order_relaxed); }
+
+static int pick_variant(int r, int m, int variant) {
+    if (variant != 0) return variant;
+    if (sweep_regpanel_supports(r, m)) return 2;
+    if (sweep_blocked_supports(r, m)) return 3;
+    return 1;
+}
+
+extern "C" size_t mf_sweep_ws_bytes(int r, int m, int64_t F, int variant) {
+    if (r <= 0 || m <= 0 || F <= 0) return 256;
+    size_t a = sweep_generic_ws_bytes(r, m, F);
+    size_t b = sweep_blocked_supports(r, m) ? sweep_blocked_ws_bytes(r, m, F) : 0;
+    int v = pick_variant(r, m, variant);
+    size_t need = v == 1 ? a : (v == 3 ? b : 0);
+    return need < 256 ? 256 : need;
+}
+
+extern "C" int mf_sweep_lu_gsm_c128(const mf_c128* A0, const mf_c128* A1, const mf_c128* A2, int64_t lda,
+                                    const mf_c128* Br, int64_t ldb, int r, int m,
+                                    const double* c0, const double* c1, const double* c2, const double* cb,
+                                    const double* zscale, int64_t F,
+                                    mf_c128* X, mf_c128* S, int* info, int variant,
+                                    void* ws, size_t ws_bytes, void* stream) {
+    if (!A0 && !A1 && !A2) MF_FAIL_ARG(1, "all three operators are NULL");
+    if (lda < r) MF_FAIL_ARG(4, "lda < r");
+    if (!Br || ldb < m) MF_FAIL_ARG(5, "Br is NULL or ldb < m");
+    if (r <= 0 || r > 1024) MF_FAIL_ARG(7, "need 0 < r <= 1024");
+    if (m <= 0 || m > MF_MAX_PORTS) MF_FAIL_ARG(8, "need 0 < m <= MF_MAX_PORTS");
+    if (!c0 || !c1 || !c2) MF_FAIL_ARG(9, "coefficient arrays must not be NULL");
+    if (!cb) MF_FAIL_ARG(12, "cb is NULL");
+    if (S && !zscale) MF_FAIL_ARG(13, "zscale is NULL but S is requested");
+    if (F < 0) MF_FAIL_ARG(14, "F < 0");
+    if (!X && !S) MF_FAIL_ARG(15, "neither X nor S requested");
+    if (variant < 0 || variant > 3) MF_FAIL_ARG(18, "variant must be 0..3");
+    if (F == 0) return 0;
+    SweepParams p;
+    p.A0 = (const cplx*)A0; p.A1 = (const cplx*)A1; p.A2 = (const cplx*)A2; p.lda = lda;
+    p.Br = (const cplx*)Br; p.ldb = ldb; p.r = r; p.m = m;
+    p.c0 = c0; p.c1 = c1; p.c2 = c2; p.cb = cb; p.zs = zscale; p.F = F;
+    p.X = (cplx*)X; p.S = (cplx*)S; p.info = info; p.ws = (cplx*)ws; p.ws_stride = 0;
+    const int v = pick_variant(r, m, variant);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (v == 2) {
+        if (!sweep_regpanel_supports(r, m)) MF_FAIL_ARG(18, "register-panel variant does not support this (r, m)");
+        return sweep_regpanel_launch(p, st);
+    }
+    if (v == 3) {
+        if (!sweep_blocked_supports(r, m)) MF_FAIL_ARG(18, "blocked variant does not support this (r, m)");
+        return sweep_blocked_launch(p, ws_bytes, st);
+    }
+    return sweep_generic_launch(p, ws_bytes, st);
+}

@@ -1,0 +1,330 @@
+// r x r device-resident factorisations used by the basis stage (CholeskyQR2 + SVD of the triangular factor,
+// the B200 replacement of `np.linalg.svd(S, full_matrices=False)[0]`, implementation.py:226/298/210) and the
+// one-off symmetrisation of the reduced operators (implementation.py:528).  All of them touch at most a few
+// MiB that stay in L2; they are latency-, not bandwidth- or flop-bound, so each is a single launch.
+#include "common.cuh"
+
+namespace {
+
+// ------------------------------------------------------------------------------------------- equilibrate
+__global__ void equilibrate_kernel(cplx* G, long long ld, int r, double shift, double* d, double* stats) {
+    extern __shared__ double ds[];
+    __shared__ double wmax[32];
+    double dev = 0.0;
+    for (int j = threadIdx.x; j < r; j += blockDim.x) {
+        double g = G[j * ld + j].x;
+        double s = (g > 0.0 && isfinite(g)) ? 1.0 / sqrt(g) : 1.0;
+        ds[j] = s; d[j] = s;
+    }
+    __syncthreads();
+    for (long long idx = threadIdx.x; idx < (long long)r * r; idx += blockDim.x) {
+        int i = (int)(idx / r), j = (int)(idx - (long long)i * r);
+        cplx v = G[i * ld + j];
+        dev = fmax(dev, fabs(v.x - (i == j ? 1.0 : 0.0)) + fabs(v.y));
+        double s = ds[i] * ds[j];
+        v.x *= s; v.y *= s;
+        if (i == j) { v.x += shift; v.y = 0.0; }
+        G[i * ld + j] = v;
+    }
+    for (int off = 16; off > 0; off >>= 1) dev = fmax(dev, __shfl_xor_sync(0xffffffffu, dev, off));
+    if ((threadIdx.x & 31) == 0) wmax[threadIdx.x >> 5] = dev;
+    __syncthreads();
+    if (threadIdx.x == 0 && stats) {
+        double mx = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) mx = fmax(mx, wmax[w]);
+        stats[0] = isfinite(mx) ? mx : 1e300;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------- potrf
+// Right-looking Cholesky G = R^H R (R upper, row-major), one CTA.
+__global__ void __launch_bounds__(1024) potrf_upper_kernel(cplx* G, long long ld, int r, int* info) {
+    __shared__ int bad;
+    if (threadIdx.x == 0) bad = 0;
+    __syncthreads();
+    for (int k = 0; k < r; ++k) {
+        double piv = G[k * ld + k].x;
+        if (!(piv > 0.0) || !isfinite(piv)) { if (threadIdx.x == 0) bad = k + 1; }
+        __syncthreads();
+        if (bad) break;
+        const double rkk = sqrt(piv), inv = 1.0 / rkk;
+        for (int j = k + threadIdx.x; j < r; j += blockDim.x) {
+            cplx v = G[k * ld + j];
+            if (j == k) v = cmake(rkk, 0.0); else { v.x *= inv; v.y *= inv; }
+            G[k * ld + j] = v;
+        }
+        __syncthreads();
+        const int w = r - (k + 1);
+        for (int idx = threadIdx.x; idx < w * w; idx += blockDim.x) {
+            int ii = idx / w, jj = idx - ii * w;
+            if (jj < ii) continue;
+            int i = k + 1 + ii, j = k + 1 + jj;
+            cplx a = G[i * ld + j];
+            cfms(a, cconj(G[k * ld + i]), G[k * ld + j]);
+            G[i * ld + j] = a;
+        }
+        __syncthreads();
+    }
+    for (int idx = threadIdx.x; idx < r * r; idx += blockDim.x) {
+        int i = idx / r, j = idx - i * r;
+        if (j < i) G[i * ld + j] = cmake(0.0, 0.0);
+    }
+    if (threadIdx.x == 0 && info) *info = bad;
+}
+
+// ------------------------------------------------------------------------------------------------- trtri
+// One warp per column j of Rinv: back substitution R x = e_j; x kept in shared memory.
+__global__ void trtri_upper_kernel(const cplx* __restrict__ R, long long ldr, int r, cplx* __restrict__ Rinv, long long ldi) {
+    extern __shared__ __align__(16) cplx xs_all[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    const int j = blockIdx.x * wpb + warp;
+    if (j >= r) return;
+    cplx* x = xs_all + (size_t)warp * r;
+    if (lane == 0) x[j] = crecip(R[j * ldr + j]);
+    __syncwarp();
+    for (int i = j - 1; i >= 0; --i) {
+        cplx acc = cmake(0.0, 0.0);
+        for (int k = i + 1 + lane; k <= j; k += 32) cfma(acc, R[i * ldr + k], x[k]);
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            acc.x += __shfl_xor_sync(0xffffffffu, acc.x, off);
+            acc.y += __shfl_xor_sync(0xffffffffu, acc.y, off);
+        }
+        if (lane == 0) { cplx v = cmul(acc, crecip(R[i * ldr + i])); x[i] = cmake(-v.x, -v.y); }
+        __syncwarp();
+    }
+    for (int i = lane; i < r; i += 32) Rinv[i * ldi + j] = (i <= j) ? x[i] : cmake(0.0, 0.0);
+}
+
+// ------------------------------------------------------------------------------------------ scale / sym
+__global__ void scale_kernel(cplx* X, long long ld, int rows, int cols, const double* d, int power, int by_rows) {
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)rows * cols) return;
+    int i = (int)(idx / cols), j = (int)(idx - (long long)i * cols);
+    double s = d[by_rows ? i : j];
+    if (power < 0) s = 1.0 / s;
+    cplx v = X[i * ld + j]; v.x *= s; v.y *= s; X[i * ld + j] = v;
+}
+
+__global__ void symmetrize_kernel(const cplx* __restrict__ A, long long lda, int r, cplx* __restrict__ As, long long lds) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= r * r) return;
+    int i = idx / r, j = idx - i * r;
+    cplx a = A[i * lda + j], b = A[j * lda + i];
+    As[i * lds + j] = cmake((a.x + b.x) / 2, (a.y + b.y) / 2);
+}
+
+// -------------------------------------------------------------------------------------------- Jacobi SVD
+// One-sided (Hestenes) Jacobi on the ROWS of X: left rotations G with G X = Sigma W^H, hence X = G^H Sigma W^H
+// and the left singular vectors are the columns of G^H.  r2 = r rounded up to even; CTA c owns one pair per
+// round of the round-robin tournament; a device-wide barrier separates rounds (cooperative launch guarantees
+// co-residency).  Layout of ws: Xw (r2 x r) | Gacc (r2 x r2) | sig (r2 doubles) | offmax (64 doubles) | counter.
+constexpr int JS_THREADS = 128;
+
+__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& epoch, unsigned nblocks) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned target = (epoch + 1u) * nblocks;
+        atomicAdd(counter, 1u);
+        while (*((volatile unsigned*)counter) < target) { __nanosleep(32); }
+        __threadfence();
+    }
+    epoch += 1u;
+    __syncthreads();
+}
+
+__device__ __forceinline__ double block_sum4(double& a, double& b, double& c, double& d, double* red) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, off); b += __shfl_xor_sync(0xffffffffu, b, off);
+        c += __shfl_xor_sync(0xffffffffu, c, off); d += __shfl_xor_sync(0xffffffffu, d, off);
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    __syncthreads();
+    if (lane == 0) { red[warp * 4 + 0] = a; red[warp * 4 + 1] = b; red[warp * 4 + 2] = c; red[warp * 4 + 3] = d; }
+    __syncthreads();
+    a = b = c = d = 0.0;
+    for (int w = 0; w < nw; ++w) { a += red[w * 4 + 0]; b += red[w * 4 + 1]; c += red[w * 4 + 2]; d += red[w * 4 + 3]; }
+    return a;
+}
+
+__global__ void __launch_bounds__(JS_THREADS)
+jacobi_svd_kernel(const cplx* __restrict__ Xin, long long ld, int r, cplx* __restrict__ U, long long ldu, double* __restrict__ sigma,
+                  int max_sweeps, double tol, int* sweeps_done, cplx* Xw, cplx* Gacc, double* sig, double* offmax, unsigned* counter) {
+    __shared__ double red[4 * (JS_THREADS / 32)];
+    const int r2 = (r + 1) & ~1;
+    const int c = blockIdx.x, nblocks = gridDim.x, tid = threadIdx.x;
+    unsigned epoch = 0;
+    // init: copy X, identity accumulator
+    for (int row = 2 * c; row < 2 * c + 2; ++row) {
+        for (int k = tid; k < r; k += JS_THREADS) Xw[(long long)row * r + k] = row < r ? Xin[row * ld + k] : cmake(0.0, 0.0);
+        for (int k = tid; k < r2; k += JS_THREADS) Gacc[(long long)row * r2 + k] = cmake(k == row ? 1.0 : 0.0, 0.0);
+    }
+    if (c == 0) for (int k = tid; k < 64; k += JS_THREADS) offmax[k] = 0.0;
+    grid_barrier(counter, epoch, nblocks);
+
+    int sweep = 0;
+    for (; sweep < max_sweeps; ++sweep) {
+        for (int round = 0; round < r2 - 1; ++round) {
+            int p, q;
+            if (c == 0) { p = r2 - 1; q = round; }
+            else { p = (round + c) % (r2 - 1); q = (round - c + (r2 - 1)) % (r2 - 1); }
+            if (p > q) { int tmp = p; p = q; q = tmp; }
+            cplx* xp = Xw + (long long)p * r; cplx* xq = Xw + (long long)q * r;
+            double a = 0.0, b = 0.0, cr = 0.0, ci = 0.0;
+            for (int k = tid; k < r; k += JS_THREADS) {
+                cplx u = __ldcg(xp + k), v = __ldcg(xq + k);   // rows were last written by other CTAs: read at L2
+                a += cnorm2(u); b += cnorm2(v);
+                cr += u.x * v.x + u.y * v.y;      // u * conj(v)
+                ci += u.y * v.x - u.x * v.y;
+            }
+            block_sum4(a, b, cr, ci, red);
+            const double cabs = hypot(cr, ci);
+            const double denom = sqrt(a) * sqrt(b);
+            const double off = denom > 0.0 ? cabs / denom : 0.0;
+            if (off > tol && cabs > 0.0) {
+                if (tid == 0) atomicMax((unsigned long long*)&offmax[sweep & 63], (unsigned long long)__double_as_longlong(off));
+                const double zeta = (b - a) / (2.0 * cabs);
+                const double tt = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+                const double cs = 1.0 / sqrt(1.0 + tt * tt), sn = cs * tt;
+                const cplx ph = cmake(cr / cabs, ci / cabs);            // e^{i phi}
+                const cplx sph = cscale(sn, ph), sphc = cscale(sn, cconj(ph));
+                for (int k = tid; k < r; k += JS_THREADS) {
+                    cplx u = __ldcg(xp + k), v = __ldcg(xq + k);
+                    xp[k] = csub(cscale(cs, u), cmul(sph, v));
+                    xq[k] = cadd(cmul(sphc, u), cscale(cs, v));
+                }
+                cplx* gp = Gacc + (long long)p * r2; cplx* gq = Gacc + (long long)q * r2;
+                for (int k = tid; k < r2; k += JS_THREADS) {
+                    cplx u = __ldcg(gp + k), v = __ldcg(gq + k);
+                    gp[k] = csub(cscale(cs, u), cmul(sph, v));
+                    gq[k] = cadd(cmul(sphc, u), cscale(cs, v));
+                }
+            }
+            grid_barrier(counter, epoch, nblocks);
+        }
+        const double worst = *((volatile double*)&offmax[sweep & 63]);
+        if (!(worst > tol)) { ++sweep; break; }
+    }
+    // singular values = row norms
+    for (int row = 2 * c; row < 2 * c + 2; ++row) {
+        double a = 0.0, z0 = 0.0, z1 = 0.0, z2 = 0.0;
+        for (int k = tid; k < r; k += JS_THREADS) a += cnorm2(__ldcg(Xw + (long long)row * r + k));
+        block_sum4(a, z0, z1, z2, red);
+        if (tid == 0) sig[row] = sqrt(a);
+    }
+    grid_barrier(counter, epoch, nblocks);
+    for (int row = 2 * c; row < 2 * c + 2; ++row) {
+        if (row >= r) continue;
+        const double s = __ldcg(sig + row);
+        int rank = 0;
+        for (int j = 0; j < r; ++j) { double sj = __ldcg(sig + j); rank += (sj > s) || (sj == s && j < row); }
+        if (tid == 0) sigma[rank] = s;
+        for (int k = tid; k < r; k += JS_THREADS) U[k * ldu + rank] = cconj(__ldcg(Gacc + (long long)row * r2 + k));
+    }
+    if (c == 0 && tid == 0 && sweeps_done) *sweeps_done = sweep;
+}
+
+}  // namespace
+
+extern "C" int mf_equilibrate_c128(mf_c128* G, int64_t ld, int r, double shift, double* d, double* stats, void* stream) {
+    if (!G || ld < r) MF_FAIL_ARG(1, "G is NULL or ld < r");
+    if (r <= 0 || r > 4096) MF_FAIL_ARG(3, "need 0 < r <= 4096");
+    if (!d) MF_FAIL_ARG(5, "d is NULL");
+    equilibrate_kernel<<<1, 1024, sizeof(double) * r, (cudaStream_t)stream>>>((cplx*)G, ld, r, shift, d, stats);
+    MF_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int mf_potrf_upper_c128(mf_c128* G, int64_t ld, int r, int* info, void* stream) {
+    if (!G || ld < r) MF_FAIL_ARG(1, "G is NULL or ld < r");
+    if (r <= 0) MF_FAIL_ARG(3, "r <= 0");
+    potrf_upper_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>((cplx*)G, ld, r, info);
+    MF_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int mf_trtri_upper_c128(const mf_c128* R, int64_t ldr, int r, mf_c128* Rinv, int64_t ldi, void* stream) {
+    if (!R || ldr < r) MF_FAIL_ARG(1, "R is NULL or ldr < r");
+    if (r <= 0 || r > 1024) MF_FAIL_ARG(3, "need 0 < r <= 1024");
+    if (!Rinv || ldi < r) MF_FAIL_ARG(4, "Rinv is NULL or ldi < r");
+    if ((const void*)R == (const void*)Rinv) MF_FAIL_ARG(4, "Rinv must not alias R");
+    const int wpb = 4;
+    const size_t smem = sizeof(cplx) * (size_t)wpb * r;
+    MF_CHECK_CUDA(cudaFuncSetAttribute(trtri_upper_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    trtri_upper_kernel<<<(r + wpb - 1) / wpb, wpb * 32, smem, (cudaStream_t)stream>>>((const cplx*)R, ldr, r, (cplx*)Rinv, ldi);
+    MF_CHECK_LAUNCH();
+    return 0;
+}
+
+static int scale_launch(mf_c128* X, int64_t ld, int rows, int cols, const double* d, int power, int by_rows, void* stream) {
+    long long total = (long long)rows * cols;
+    if (total == 0) return 0;
+    scale_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>((cplx*)X, ld, rows, cols, d, power, by_rows);
+    g_mf_launches.fetch_add(1, std::memory_order_relaxed);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { snprintf(g_mf_err, sizeof(g_mf_err), "scale: launch failed: %s", cudaGetErrorString(e)); return (int)e; }
+    return 0;
+}
+
+extern "C" int mf_scale_cols_c128(mf_c128* X, int64_t ld, int rows, int cols, const double* d, int power, void* stream) {
+    if (!X || ld < cols) MF_FAIL_ARG(1, "X is NULL or ld < cols");
+    if (!d) MF_FAIL_ARG(5, "d is NULL");
+    if (power != 1 && power != -1) MF_FAIL_ARG(6, "power must be +1 or -1");
+    return scale_launch(X, ld, rows, cols, d, power, 0, stream);
+}
+
+extern "C" int mf_scale_rows_c128(mf_c128* X, int64_t ld, int rows, int cols, const double* d, int power, void* stream) {
+    if (!X || ld < cols) MF_FAIL_ARG(1, "X is NULL or ld < cols");
+    if (!d) MF_FAIL_ARG(5, "d is NULL");
+    if (power != 1 && power != -1) MF_FAIL_ARG(6, "power must be +1 or -1");
+    return scale_launch(X, ld, rows, cols, d, power, 1, stream);
+}
+
+extern "C" int mf_symmetrize_c128(const mf_c128* A, int64_t lda, int r, mf_c128* As, int64_t lds, void* stream) {
+    if (!A || lda < r) MF_FAIL_ARG(1, "A is NULL or lda < r");
+    if (r <= 0) MF_FAIL_ARG(3, "r <= 0");
+    if (!As || lds < r) MF_FAIL_ARG(4, "As is NULL or lds < r");
+    if ((const void*)A == (const void*)As) MF_FAIL_ARG(4, "As must not alias A");
+    symmetrize_kernel<<<(r * r + 255) / 256, 256, 0, (cudaStream_t)stream>>>((const cplx*)A, lda, r, (cplx*)As, lds);
+    MF_CHECK_LAUNCH();
+    return 0;
+}
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+extern "C" size_t mf_jacobi_svd_ws_bytes(int r) {
+    if (r <= 0) return 256;
+    size_t r2 = (size_t)((r + 1) & ~1);
+    return align_up(sizeof(cplx) * r2 * r, 256) + align_up(sizeof(cplx) * r2 * r2, 256) + align_up(sizeof(double) * r2, 256) + 64 * sizeof(double) + 256;
+}
+
+extern "C" int mf_jacobi_svd_c128(mf_c128* X, int64_t ld, int r, mf_c128* U, int64_t ldu, double* sigma, int max_sweeps,
+                                  double tol, int* sweeps_done, void* ws, size_t ws_bytes, void* stream) {
+    if (!X || ld < r) MF_FAIL_ARG(1, "X is NULL or ld < r");
+    if (r <= 0 || r > 2048) MF_FAIL_ARG(3, "need 0 < r <= 2048");
+    if (!U || ldu < r) MF_FAIL_ARG(4, "U is NULL or ldu < r");
+    if (!sigma) MF_FAIL_ARG(6, "sigma is NULL");
+    if (max_sweeps <= 0 || max_sweeps > 64) MF_FAIL_ARG(7, "need 0 < max_sweeps <= 64");
+    if (!ws || ws_bytes < mf_jacobi_svd_ws_bytes(r)) MF_FAIL_ARG(10, "workspace too small (mf_jacobi_svd_ws_bytes)");
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t r2 = (size_t)((r + 1) & ~1);
+    char* base = (char*)ws;
+    cplx* Xw = (cplx*)base; base += align_up(sizeof(cplx) * r2 * r, 256);
+    cplx* Gacc = (cplx*)base; base += align_up(sizeof(cplx) * r2 * r2, 256);
+    double* sig = (double*)base; base += align_up(sizeof(double) * r2, 256);
+    double* offmax = (double*)base; base += 64 * sizeof(double);
+    unsigned* counter = (unsigned*)base;
+    const int grid = (int)(r2 / 2);
+    int per_sm = 0;
+    MF_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, jacobi_svd_kernel, JS_THREADS, 0));
+    if (grid > per_sm * mf_num_sms()) MF_FAIL_ARG(3, "r too large for a co-resident Jacobi grid");
+    MF_CHECK_CUDA(cudaMemsetAsync(counter, 0, 256, st));
+    const cplx* Xin = (const cplx*)X; long long ldl = ld, ldul = ldu; cplx* Uc = (cplx*)U;
+    void* args[] = {(void*)&Xin, (void*)&ldl, (void*)&r, (void*)&Uc, (void*)&ldul, (void*)&sigma, (void*)&max_sweeps, (void*)&tol,
+                    (void*)&sweeps_done, (void*)&Xw, (void*)&Gacc, (void*)&sig, (void*)&offmax, (void*)&counter};
+    MF_CHECK_CUDA(cudaLaunchCooperativeKernel((const void*)jacobi_svd_kernel, dim3(grid), dim3(JS_THREADS), args, 0, st));
+    g_mf_launches.fetch_add(1, std::memory_order_relaxed);
+    return 0;
+}

@@ -1,0 +1,357 @@
+"""Device-side building blocks of the reduced-order sweep path.
+
+Everything numerical happens in ``libmorfem_b200.so`` (hand-written sm_100a CUDA, ``morfem_b200/csrc``);
+PyTorch supplies device memory (tensors are only allocators / ``data_ptr()`` hand-off), the current stream, and
+``torch.distributed`` for the r x r all-reduces, the halo exchange and the result gather.  There is no CPU
+fallback: every function raises if CUDA or the library is unavailable.
+
+Reference call sites replaced (paths relative to the reference repo):
+  orthonormalize        np.linalg.svd(S, full_matrices=False)[0]     implementation.py:226, :298, :210
+  spmm / gemm_tn        (q_t @ a_i) @ q                              implementation.py:181-183
+  project_rhs           q_t @ b                                      implementation.py:184
+  sweep                 solve_finite_element_method + GSM loop       implementation.py:189-194, test_helpers.py:60-65
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _ffi
+
+C128 = torch.complex128
+
+
+def require_cuda() -> torch.device:
+    if not torch.cuda.is_available():
+        raise _ffi.MorfemB200Error("morfem_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _check_mat(t: torch.Tensor, name: str):
+    if t.dtype != C128 or not t.is_cuda or t.dim() != 2 or t.stride(1) != 1:
+        raise ValueError(f"{name}: expected a row-major complex128 CUDA matrix, got {t.dtype} {tuple(t.shape)} strides {t.stride()}")
+
+
+def to_device_c128(a, device=None) -> torch.Tensor:
+    """Host ndarray (real or complex) -> contiguous complex128 device tensor."""
+    device = device or require_cuda()
+    arr = np.ascontiguousarray(np.asarray(a), dtype=np.complex128)
+    return torch.from_numpy(arr).to(device, non_blocking=False)
+
+
+class _Workspaces:
+    """Grow-only byte buffers keyed by purpose, per device (the C ABI never allocates)."""
+
+    def __init__(self):
+        self._bufs = {}
+
+    def get(self, key: str, nbytes: int, device) -> torch.Tensor:
+        k = (key, str(device))
+        buf = self._bufs.get(k)
+        if buf is None or buf.numel() < nbytes:
+            buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+            self._bufs[k] = buf
+        return buf
+
+    def clear(self):
+        self._bufs.clear()
+
+
+workspaces = _Workspaces()
+
+
+# ------------------------------------------------------------------------------------------ dense wrappers
+def gemm_tn(a: torch.Tensor, b: torch.Tensor, conj: bool = False, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``op(a)^T b`` (ra x rb), reduction over the rows; ``conj`` selects ``a^H``."""
+    lib = _ffi.load()
+    _check_mat(a, "a"); _check_mat(b, "b")
+    n, ra = a.shape
+    rb = b.shape[1]
+    if b.shape[0] != n:
+        raise ValueError("gemm_tn: row counts differ")
+    if out is None:
+        out = torch.empty((ra, rb), dtype=C128, device=a.device)
+    nbytes = lib.mf_gemm_tn_ws_bytes(ra, rb, n)
+    ws = workspaces.get("gemm_tn", nbytes, a.device)
+    _ffi.check(lib.mf_gemm_tn_c128(_ptr(a), a.stride(0), ra, _ptr(b), b.stride(0), rb, n, int(conj), _ptr(out), out.stride(0),
+                                   _ptr(ws), ws.numel(), _stream()), "mf_gemm_tn_c128")
+    return out
+
+
+def gemm_nn(a: torch.Tensor, w: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``a @ w`` for a tall ``a`` (n x ra) and a small ``w`` (ra x rb)."""
+    lib = _ffi.load()
+    _check_mat(a, "a"); _check_mat(w, "w")
+    n, ra = a.shape
+    if w.shape[0] != ra:
+        raise ValueError("gemm_nn: inner dimensions differ")
+    rb = w.shape[1]
+    if out is None:
+        out = torch.empty((n, rb), dtype=C128, device=a.device)
+    _ffi.check(lib.mf_gemm_nn_c128(_ptr(a), a.stride(0), n, ra, _ptr(w), w.stride(0), rb, _ptr(out), out.stride(0), _stream()),
+               "mf_gemm_nn_c128")
+    return out
+
+
+def symmetrize(a: torch.Tensor) -> torch.Tensor:
+    """``(a + a.T) / 2`` -- implementation.py:528, hoisted out of the per-point loop."""
+    lib = _ffi.load()
+    _check_mat(a, "a")
+    r = a.shape[0]
+    out = torch.empty((r, r), dtype=C128, device=a.device)
+    _ffi.check(lib.mf_symmetrize_c128(_ptr(a), a.stride(0), r, _ptr(out), out.stride(0), _stream()), "mf_symmetrize_c128")
+    return out
+
+
+# ----------------------------------------------------------------------------------------- sparse operands
+@dataclass
+class DeviceCSR:
+    """CSR operand of the SpMM.  For a reference ``csc_array`` ``a`` the CSC arrays *are* the CSR arrays of
+    ``a.T``, which is what ``q_t @ a`` multiplies by (scipy ``_rmatmul_dispatch``)."""
+    rowptr: torch.Tensor   # int32, nrows + 1 (rebased to 0 for a row slice)
+    colidx: torch.Tensor   # int32, global column index = row of Q
+    vals: torch.Tensor     # float64 or complex128
+    nrows: int
+    ncols: int
+    row0: int = 0          # first global row of this slice
+
+    @property
+    def nnz(self) -> int:
+        return int(self.colidx.numel())
+
+    @property
+    def is_real(self) -> bool:
+        return self.vals.dtype == torch.float64
+
+
+def csr_of_transpose(a_csc, device=None, row_range=None) -> DeviceCSR:
+    """Upload the CSR view of ``a.T`` for a scipy ``csc_array``/``csc_matrix`` ``a`` (no conversion work: the
+    three CSC arrays are reused).  ``row_range=(lo, hi)`` uploads only rows lo..hi-1 of ``a.T``."""
+    import scipy.sparse as sp
+    device = device or require_cuda()
+    a = a_csc if sp.issparse(a_csc) and a_csc.format == "csc" else sp.csc_array(a_csc)
+    n_rows_t = a.shape[1]
+    lo, hi = (0, n_rows_t) if row_range is None else row_range
+    indptr = np.asarray(a.indptr)
+    s, e = int(indptr[lo]), int(indptr[hi])
+    if e - s >= 2 ** 31 or a.shape[0] >= 2 ** 31:
+        raise ValueError("operator too large for int32 indices")
+    rowptr = (indptr[lo:hi + 1] - indptr[lo]).astype(np.int32)
+    colidx = np.asarray(a.indices[s:e], dtype=np.int32)
+    data = np.asarray(a.data[s:e])
+    vals = np.ascontiguousarray(data, dtype=np.complex128 if np.iscomplexobj(data) else np.float64)
+    return DeviceCSR(torch.from_numpy(rowptr).to(device), torch.from_numpy(colidx).to(device),
+                     torch.from_numpy(vals).to(device), hi - lo, a.shape[0], lo)
+
+
+def spmm(a: DeviceCSR, q: torch.Tensor, out: Optional[torch.Tensor] = None, col_offset: int = 0) -> torch.Tensor:
+    """``Y = A Q`` for the CSR operand; ``q`` holds rows ``col_offset ..`` of the global Q (halo window)."""
+    lib = _ffi.load()
+    _check_mat(q, "q")
+    r = q.shape[1]
+    if out is None:
+        out = torch.empty((a.nrows, r), dtype=C128, device=q.device)
+    colidx = a.colidx if col_offset == 0 else a.colidx - col_offset
+    _ffi.check(lib.mf_spmm_csr_c128(_ptr(a.rowptr), _ptr(colidx), _ptr(a.vals), int(a.is_real), a.nrows, _ptr(q), q.stride(0), r,
+                                    _ptr(out), out.stride(0), _stream()), "mf_spmm_csr_c128")
+    return out
+
+
+@dataclass
+class DeviceCSC:
+    colptr: torch.Tensor
+    rowidx: torch.Tensor
+    vals: torch.Tensor
+    nrows: int
+    ncols: int
+
+    @property
+    def is_real(self) -> bool:
+        return self.vals.dtype == torch.float64
+
+
+def csc_to_device(b_csc, device=None) -> DeviceCSC:
+    import scipy.sparse as sp
+    device = device or require_cuda()
+    b = b_csc if sp.issparse(b_csc) and b_csc.format == "csc" else sp.csc_array(b_csc)
+    data = np.asarray(b.data)
+    vals = np.ascontiguousarray(data, dtype=np.complex128 if np.iscomplexobj(data) else np.float64)
+    return DeviceCSC(torch.from_numpy(np.asarray(b.indptr, dtype=np.int32)).to(device),
+                     torch.from_numpy(np.asarray(b.indices, dtype=np.int32)).to(device),
+                     torch.from_numpy(vals).to(device), b.shape[0], b.shape[1])
+
+
+def project_rhs(b: DeviceCSC, q: torch.Tensor, row0: int = 0, conj: bool = False) -> torch.Tensor:
+    """``q^T b`` (r x m) restricted to the rows ``row0 .. row0 + q.shape[0]`` held locally."""
+    lib = _ffi.load()
+    _check_mat(q, "q")
+    r = q.shape[1]
+    out = torch.empty((r, b.ncols), dtype=C128, device=q.device)
+    _ffi.check(lib.mf_project_rhs_c128(_ptr(b.colptr), _ptr(b.rowidx), _ptr(b.vals), int(b.is_real), b.ncols, _ptr(q), q.stride(0), r,
+                                       row0, q.shape[0], int(conj), _ptr(out), out.stride(0), _stream()), "mf_project_rhs_c128")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ stage 1
+def _allreduce(t: torch.Tensor, group) -> None:
+    if group is None:
+        return
+    import torch.distributed as dist
+    dist.all_reduce(torch.view_as_real(t), op=dist.ReduceOp.SUM, group=group)
+
+
+@dataclass
+class BasisInfo:
+    sigma: np.ndarray          # singular values of the snapshot block (descending)
+    passes: int                # Cholesky-QR passes used
+    shifts: list               # diagonal shift used in each pass (0 = plain Cholesky)
+    jacobi_sweeps: int
+    kept: int                  # columns kept after truncation
+
+
+def orthonormalize(s: torch.Tensor, truncation_tol: float = 0.0, group=None, n_global: Optional[int] = None,
+                   max_passes: int = 6) -> tuple[torch.Tensor, BasisInfo]:
+    """Orthonormal basis of span(S) with columns ordered like the left singular vectors of S.
+
+    B200 replacement of ``np.linalg.svd(S, full_matrices=False)[0]`` (implementation.py:226/298/210):
+    Cholesky-QR passes ``G = X^H X`` (DMMA, all-reduced over row shards) -> equilibrated (shifted if needed)
+    Cholesky -> ``X <- X R^-1`` until the input of a pass is already near-orthonormal (CholeskyQR2, or shifted
+    CholeskyQR3 for cond(S) >~ 1e8); then a one-sided Jacobi SVD of the accumulated triangular factor
+    ``R = U_r Sigma V^H`` whose rotation ``U_r`` is folded into the last application.  Columns of the result equal
+    the reference's ``U`` up to sign (rotations inside clustered singular subspaces).  ``truncation_tol > 0``
+    drops directions with ``sigma_j <= tol * sigma_0`` (default 0 keeps all r, like the reference).
+    """
+    lib = _ffi.load()
+    _check_mat(s, "s")
+    dev = s.device
+    n_loc, r = s.shape
+    eps = np.finfo(np.float64).eps
+    d = torch.empty(r, dtype=torch.float64, device=dev)
+    stats = torch.zeros(2, dtype=torch.float64, device=dev)
+    info = torch.zeros(1, dtype=torch.int32, device=dev)
+    x = s
+    r_tot = None
+    shifts = []
+    bufs = [None, None]
+    for p in range(max_passes):
+        g = gemm_tn(x, x, conj=True)
+        _allreduce(g, group)
+        shift = 0.0
+        while True:
+            gw = g.clone()
+            _ffi.check(lib.mf_equilibrate_c128(_ptr(gw), gw.stride(0), r, shift, _ptr(d), _ptr(stats), _stream()), "mf_equilibrate_c128")
+            _ffi.check(lib.mf_potrf_upper_c128(_ptr(gw), gw.stride(0), r, _ptr(info), _stream()), "mf_potrf_upper_c128")
+            if int(info.item()) == 0:
+                break
+            shift = 64.0 * eps * r if shift == 0.0 else shift * 100.0
+            if shift > 1e-2:
+                raise _ffi.MorfemB200Error("orthonormalize: Cholesky breakdown persists (snapshot block numerically rank deficient "
+                                           "beyond what shifted CholeskyQR can repair)")
+        shifts.append(shift)
+        departure = float(stats[0].item())
+        # R = Rtilde D^-1 (undo the equilibration), Rinv = R^-1
+        _ffi.check(lib.mf_scale_cols_c128(_ptr(gw), gw.stride(0), r, r, _ptr(d), -1, _stream()), "mf_scale_cols_c128")
+        rinv = torch.empty((r, r), dtype=C128, device=dev)
+        _ffi.check(lib.mf_trtri_upper_c128(_ptr(gw), gw.stride(0), r, _ptr(rinv), rinv.stride(0), _stream()), "mf_trtri_upper_c128")
+        r_tot = gw if r_tot is None else gemm_nn(gw, r_tot)
+        final = (departure < 0.1 and shift == 0.0) or p == max_passes - 1
+        if final:
+            u = torch.empty((r, r), dtype=C128, device=dev)
+            sigma = torch.empty(r, dtype=torch.float64, device=dev)
+            sweeps = torch.zeros(1, dtype=torch.int32, device=dev)
+            nbytes = lib.mf_jacobi_svd_ws_bytes(r)
+            ws = workspaces.get("jacobi", nbytes, dev)
+            _ffi.check(lib.mf_jacobi_svd_c128(_ptr(r_tot), r_tot.stride(0), r, _ptr(u), u.stride(0), _ptr(sigma), 40, 4.0 * eps,
+                                              _ptr(sweeps), _ptr(ws), ws.numel(), _stream()), "mf_jacobi_svd_c128")
+            sig = sigma.cpu().numpy()
+            keep = r
+            if truncation_tol > 0.0 and sig[0] > 0.0:
+                keep = max(1, int(np.count_nonzero(sig > truncation_tol * sig[0])))
+            w = gemm_nn(rinv, u[:, :keep] if keep < r else u)
+            q = gemm_nn(x, w)
+            return q, BasisInfo(sig, p + 1, shifts, int(sweeps.item()), keep)
+        tgt = p % 2
+        if bufs[tgt] is None:
+            bufs[tgt] = torch.empty((n_loc, r), dtype=C128, device=dev)
+        x = gemm_nn(x, rinv, out=bufs[tgt])
+    raise AssertionError("unreachable")
+
+
+# ------------------------------------------------------------------------------------------- stages 3 + 4
+@dataclass
+class SweepResult:
+    x: Optional[torch.Tensor]       # (F, r, m) complex128 or None
+    gsm: Optional[torch.Tensor]     # (F, m, m) complex128 or None
+    info: torch.Tensor              # (F,) int32: 0 or 1-based index of the first zero pivot
+
+
+def sweep(a0s: Optional[torch.Tensor], a1s: Optional[torch.Tensor], a2s: Optional[torch.Tensor], br: torch.Tensor,
+          c0: torch.Tensor, c1: torch.Tensor, c2: torch.Tensor, cb: torch.Tensor, zscale: Optional[torch.Tensor],
+          want_x: bool = True, want_gsm: bool = True, variant: int = 0,
+          x_out: Optional[torch.Tensor] = None, gsm_out: Optional[torch.Tensor] = None) -> SweepResult:
+    """Batched reduced solves + S-parameters for the points described by the coefficient arrays.
+
+    Operators must already be symmetrised (``symmetrize``); ``None`` stands for an all-zero operator (the
+    reference projects and adds an empty ``a1`` -- test_helpers.py:57 -- which contributes exactly zero).
+    """
+    lib = _ffi.load()
+    ops = [o for o in (a0s, a1s, a2s) if o is not None]
+    if not ops:
+        raise ValueError("sweep: all operators are None")
+    for o in ops:
+        _check_mat(o, "operator")
+    _check_mat(br, "br")
+    r, m = br.shape
+    lda = ops[0].stride(0)
+    if any(o.stride(0) != lda or o.shape != (r, r) for o in ops):
+        raise ValueError("sweep: operators must share shape (r, r) and leading dimension")
+    nf = int(c0.numel())
+    dev = br.device
+    for c in (c0, c1, c2, cb) + ((zscale,) if zscale is not None else ()):
+        if c.dtype != torch.float64 or not c.is_cuda or c.numel() != nf or not c.is_contiguous():
+            raise ValueError("sweep: coefficient arrays must be contiguous float64 CUDA tensors of equal length")
+    x = (x_out if x_out is not None else torch.empty((nf, r, m), dtype=C128, device=dev)) if want_x else None
+    gsm = (gsm_out if gsm_out is not None else torch.empty((nf, m, m), dtype=C128, device=dev)) if want_gsm else None
+    info = torch.zeros(nf, dtype=torch.int32, device=dev)
+    nbytes = lib.mf_sweep_ws_bytes(r, m, nf, variant)
+    ws = workspaces.get("sweep", nbytes, dev)
+    _ffi.check(lib.mf_sweep_lu_gsm_c128(_ptr(a0s), _ptr(a1s), _ptr(a2s), lda, _ptr(br), br.stride(0), r, m,
+                                        _ptr(c0), _ptr(c1), _ptr(c2), _ptr(cb), _ptr(zscale), nf,
+                                        _ptr(x), _ptr(gsm), _ptr(info), variant, _ptr(ws), ws.numel(), _stream()),
+               "mf_sweep_lu_gsm_c128")
+    return SweepResult(x, gsm, info)
+
+
+def gsm(x: torch.Tensor, bmat: torch.Tensor, cb: torch.Tensor, zscale: torch.Tensor) -> torch.Tensor:
+    """Stage 4 alone: S-parameters from given solutions ``x`` (F, r, m) and port matrix ``bmat`` (r, m)."""
+    lib = _ffi.load()
+    nf, r, m = x.shape
+    out = torch.empty((nf, m, m), dtype=C128, device=x.device)
+    _ffi.check(lib.mf_gsm_c128(_ptr(x), _ptr(bmat), bmat.stride(0), r, m, _ptr(cb), _ptr(zscale), nf, _ptr(out), _stream()), "mf_gsm_c128")
+    return out
+
+
+def estimator(x: torch.Tensor, g_blocks, h_blocks, bb: Optional[torch.Tensor],
+              c0: torch.Tensor, c1: torch.Tensor, c2: torch.Tensor, cb: torch.Tensor) -> torch.Tensor:
+    """Greedy residual estimator (implementation.py:424-441) for all points; ``g_blocks`` is a 3x3 nested list and
+    ``h_blocks`` a list of 3 device matrices (``None`` = zero block)."""
+    lib = _ffi.load()
+    nf, r, m = x.shape
+    garr = (ctypes.c_void_p * 9)(*[None if g_blocks[a][b] is None else g_blocks[a][b].data_ptr() for a in range(3) for b in range(3)])
+    harr = (ctypes.c_void_p * 3)(*[None if h is None else h.data_ptr() for h in h_blocks])
+    err = torch.empty(nf, dtype=torch.float64, device=x.device)
+    _ffi.check(lib.mf_estimator_c128(_ptr(x), r, m, nf, ctypes.cast(garr, ctypes.c_void_p), ctypes.cast(harr, ctypes.c_void_p), _ptr(bb),
+                                     _ptr(c0), _ptr(c1), _ptr(c2), _ptr(cb), _ptr(err), _stream()), "mf_estimator_c128")
+    return err

@@ -1,0 +1,109 @@
+"""Drop-in mirror of the reference's ``test_helpers.py`` (the electromagnetic post-processing used by its
+example driver), backed by the B200 kernels.  Citations are into ``/root/reference/test_helpers.py``.
+
+    generalized_scattering_matrix(frequency_point, e, b) -> (M, M) complex                       :9-14
+    equally_distributed_points(source, amount)                                                   :17-22
+    finite_element_method_gsm(frequency_points, gate_count, in_c, in_gamma, in_b)                 :25-50
+    finite_element_method_model_order_reduction_gsm(frequency_points, gate_count, ...)            :53-67
+    b_coefficient(t)                                                                             :70-72
+
+``finite_element_method_model_order_reduction_gsm`` runs stages 2-4 fused on the device: the reduced sweep
+kernel evaluates the S-parameters in its epilogue, so the solutions never leave the GPU.
+"""
+from __future__ import annotations
+
+import math
+import time
+
+import numpy as np
+from scipy.constants import pi, epsilon_0, c as c_lightspeed
+from scipy.sparse import csc_array, issparse
+
+from . import implementation as impl
+from .implementation import ModelDefinition, morfem, solve_finite_element_method  # noqa: F401  (re-exported like the reference)
+
+
+def b_coefficient(t: float):
+    """Port normalisation (test_helpers.py:70-72); scalar only, raises ValueError below the TE cutoff."""
+    kte = 54.5976295582387
+    return math.sqrt(math.sqrt(((2 * pi * t) / c_lightspeed) ** 2 - kte ** 2) / t)
+
+
+def _dense(a):
+    return a.toarray() if issparse(a) else np.asarray(a)
+
+
+def generalized_scattering_matrix(frequency_point: float, e, b):
+    """S-parameters of one frequency point from the field solution ``e`` (r x M) and scaled port matrix ``b``
+    (r x M): ``Z = j 2 pi f eps0 e^T b``, ``S = 2 (I + Z^-1)^-1 - I`` (test_helpers.py:9-14), evaluated on the GPU."""
+    return scattering_sweep(np.array([frequency_point], dtype=np.float64), _dense(e)[None, ...], _dense(b), np.ones(1))[0]
+
+
+def scattering_sweep(frequency_points, x, b_matrix, cb) -> np.ndarray:
+    """Batched form of the loop at test_helpers.py:60-65 for host inputs: ``x`` (F, r, M), ``b_matrix`` (r, M),
+    ``cb[i]`` the per-point port coefficient.  Returns (F, M, M) complex."""
+    from . import device as dv
+    import torch
+    dev = dv.require_cuda()
+    f = np.asarray(frequency_points, dtype=np.float64)
+    xd = dv.to_device_c128(x, dev)
+    bd = dv.to_device_c128(b_matrix, dev)
+    cbd = torch.from_numpy(np.ascontiguousarray(cb, dtype=np.float64)).to(dev)
+    zs = torch.from_numpy(np.ascontiguousarray(2 * pi * f * epsilon_0)).to(dev)
+    gsm = dv.gsm(xd, bd, cbd, zs).cpu().numpy()
+    if not np.all(np.isfinite(gsm)):
+        raise np.linalg.LinAlgError("Singular matrix")    # np.linalg.inv raises on singular input (test_helpers.py:11, :13)
+    return gsm
+
+
+def equally_distributed_points(source: np.ndarray, amount: int):
+    """test_helpers.py:17-22"""
+    if amount > source.size:
+        raise Exception("amount can't be greater than the number of points in the source")
+    indices = np.linspace(0, source.size - 1, amount, dtype=int)
+    return source[indices]
+
+
+def finite_element_method_gsm(frequency_points, gate_count, in_c, in_gamma, in_b):
+    """Full-order reference sweep (test_helpers.py:25-50): one SuperLU factorisation per frequency on the host
+    (outside the hot path by the north star), S-parameters batched on the device."""
+    md = ModelDefinition(frequency_points, in_c, csc_array(in_c.shape), in_gamma, in_b,
+                         lambda t: 1, lambda t: t, lambda t: t ** 2, lambda t: b_coefficient(t))
+    start = time.time()
+    x_in_domain = solve_finite_element_method(md)
+    if impl.VERBOSE:
+        print("No MOR: ", time.time() - start, " s")
+    cb = impl.coefficient_array(b_coefficient, frequency_points)
+    return scattering_sweep(frequency_points, x_in_domain, _dense(in_b), cb)
+
+
+def finite_element_method_model_order_reduction_gsm(frequency_points, gate_count, in_c, in_gamma, in_b,
+                                                    return_details: bool = False):
+    """Reduced-order S-parameter sweep (test_helpers.py:53-67).
+
+    Reference: ``morfem(...)`` then a Python loop of ``generalized_scattering_matrix``.  Here: basis (greedy or
+    equally distributed, per the ``implementation`` flags), projection, then ONE fused launch that assembles,
+    factorises and solves every reduced system and evaluates the S-parameters in its epilogue."""
+    from . import device as dv
+    frequency_points = np.asarray(frequency_points, dtype=np.float64)
+    in_a1 = csc_array(in_c.shape)
+    md = ModelDefinition(frequency_points, in_c, in_a1, in_gamma, in_b, lambda t: 1., lambda t: t, lambda t: t ** 2,
+                         lambda t: b_coefficient(t))
+    start = time.time()
+    if impl.USE_EQUALLY_DISTRIBUTED:
+        qd = dv.to_device_c128(impl.projection_base_equally_distributed(md))
+    else:
+        qd = impl.projection_base(md, _return_device=True)
+    ops = impl._DeviceOperators(md)
+    a0_r, a1_r, a2_r, b_r = ops.project(qd)
+    res = impl._sweep_device(frequency_points, [a0_r, a1_r, a2_r], b_r, md.t_a0, md.t_a1, md.t_a2, md.t_b,
+                             want_x=return_details, want_gsm=True)
+    gsm = res.gsm.cpu().numpy()
+    if impl.VERBOSE:
+        print("MOR: ", time.time() - start, " s")
+    impl._warn_singular(res.info.cpu().numpy())
+    if gate_count != gsm.shape[1]:
+        raise ValueError(f"could not broadcast input array from shape {gsm.shape[1:]} into shape {(gate_count, gate_count)}")
+    if return_details:
+        return gsm, res, qd
+    return gsm

@@ -1,0 +1,165 @@
+"""GPU parity tests of the individual kernels, through the C ABI (ctypes), against numpy/scipy and the oracle.
+
+Tolerances: the north star asks for 1e-10 relative in complex128 on reduced matrices and S-parameters; dense
+contractions are checked much tighter (they are plain sums of products)."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    return np.linalg.norm(np.asarray(a) - np.asarray(b)) / max(np.linalg.norm(b), 1e-300)
+
+
+def crandn(rng, *shape):
+    return rng.standard_normal(shape) + 1j * rng.standard_normal(shape)
+
+
+@pytest.fixture(scope="module")
+def dv():
+    from morfem_b200 import device
+    device.require_cuda()
+    return device
+
+
+@pytest.mark.parametrize("n,ra,rb,conj", [(1000, 24, 40, False), (4099, 64, 64, True), (777, 5, 3, True),
+                                          (20000, 96, 130, False), (33, 256, 256, True), (1, 8, 8, False)])
+def test_gemm_tn(dv, n, ra, rb, conj):
+    rng = np.random.default_rng(n + ra)
+    a, b = crandn(rng, n, ra), crandn(rng, n, rb)
+    out = dv.gemm_tn(dv.to_device_c128(a), dv.to_device_c128(b), conj=conj).cpu().numpy()
+    ref = (a.conj().T if conj else a.T) @ b
+    assert rel(out, ref) < 1e-13
+
+
+def test_gemm_tn_deterministic_and_strided(dv):
+    rng = np.random.default_rng(5)
+    big = dv.to_device_c128(crandn(rng, 3000, 80))
+    a, b = big[:, :48], big[:, 16:80]          # strided views (lda = 80)
+    o1 = dv.gemm_tn(a, b, conj=True).cpu().numpy()
+    o2 = dv.gemm_tn(a, b, conj=True).cpu().numpy()
+    assert np.array_equal(o1, o2)              # fixed-order reduction of the split partials
+    h = big.cpu().numpy()
+    assert rel(o1, h[:, :48].conj().T @ h[:, 16:80]) < 1e-13
+
+
+@pytest.mark.parametrize("n,ra,rb", [(1000, 24, 40), (129, 64, 64), (5000, 100, 7), (130, 256, 256), (64, 3, 2)])
+def test_gemm_nn(dv, n, ra, rb):
+    rng = np.random.default_rng(n)
+    a, w = crandn(rng, n, ra), crandn(rng, ra, rb)
+    out = dv.gemm_nn(dv.to_device_c128(a), dv.to_device_c128(w)).cpu().numpy()
+    assert rel(out, a @ w) < 1e-13
+
+
+@pytest.mark.parametrize("r", [1, 2, 7, 16, 33, 64, 150])
+def test_cholesky_and_triangular_inverse(dv, r):
+    from morfem_b200 import _ffi
+    lib = _ffi.load()
+    rng = np.random.default_rng(r)
+    x = crandn(rng, 4 * r + 3, r)
+    g = x.conj().T @ x
+    gd = dv.to_device_c128(g)
+    info = torch.zeros(1, dtype=torch.int32, device="cuda")
+    _ffi.check(lib.mf_potrf_upper_c128(dv._ptr(gd), gd.stride(0), r, dv._ptr(info), dv._stream()))
+    assert int(info.item()) == 0
+    rr = gd.cpu().numpy()
+    ref = np.linalg.cholesky(g).conj().T
+    assert rel(rr, ref) < 1e-11
+    rinv = torch.empty_like(gd)
+    _ffi.check(lib.mf_trtri_upper_c128(dv._ptr(gd), gd.stride(0), r, dv._ptr(rinv), rinv.stride(0), dv._stream()))
+    assert rel(rinv.cpu().numpy() @ rr, np.eye(r)) < 1e-10
+
+
+def test_cholesky_reports_breakdown(dv):
+    from morfem_b200 import _ffi
+    lib = _ffi.load()
+    g = np.diag([1.0, 2.0, -1.0, 3.0]).astype(complex)
+    gd = dv.to_device_c128(g)
+    info = torch.zeros(1, dtype=torch.int32, device="cuda")
+    _ffi.check(lib.mf_potrf_upper_c128(dv._ptr(gd), gd.stride(0), 4, dv._ptr(info), dv._stream()))
+    assert int(info.item()) == 3
+
+
+@pytest.mark.parametrize("r,cmplx", [(1, False), (2, True), (5, True), (16, False), (31, True), (64, True), (128, False)])
+def test_jacobi_svd(dv, r, cmplx):
+    from morfem_b200 import _ffi
+    lib = _ffi.load()
+    rng = np.random.default_rng(100 + r)
+    m = crandn(rng, r, r) if cmplx else rng.standard_normal((r, r)).astype(complex)
+    m = np.triu(m) * (10.0 ** (-4.0 * np.arange(r) / max(r, 1)))[None, :]      # graded, upper triangular like an R factor
+    md = dv.to_device_c128(m)
+    u = torch.empty_like(md)
+    sigma = torch.empty(r, dtype=torch.float64, device="cuda")
+    sweeps = torch.zeros(1, dtype=torch.int32, device="cuda")
+    ws = torch.empty(lib.mf_jacobi_svd_ws_bytes(r), dtype=torch.uint8, device="cuda")
+    _ffi.check(lib.mf_jacobi_svd_c128(dv._ptr(md), md.stride(0), r, dv._ptr(u), u.stride(0), dv._ptr(sigma), 40, 1e-15,
+                                      dv._ptr(sweeps), dv._ptr(ws), ws.numel(), dv._stream()))
+    uh, sh = u.cpu().numpy(), sigma.cpu().numpy()
+    u_ref, s_ref, _ = np.linalg.svd(m)
+    assert np.all(np.diff(sh) <= 0)
+    assert np.max(np.abs(sh - s_ref) / s_ref) < 1e-12
+    assert rel(uh.conj().T @ uh, np.eye(r)) < 1e-13
+    # U^H M must have orthogonal rows with norms sigma
+    t = uh.conj().T @ m
+    assert rel(t @ t.conj().T, np.diag(sh ** 2)) < 1e-12
+    assert 1 <= int(sweeps.item()) <= 40
+
+
+def test_symmetrize(dv):
+    rng = np.random.default_rng(0)
+    a = crandn(rng, 37, 37)
+    out = dv.symmetrize(dv.to_device_c128(a)).cpu().numpy()
+    assert np.array_equal(out, (a + a.T) / 2)
+
+
+@pytest.mark.parametrize("r", [8, 24, 64, 100, 256, 300])
+@pytest.mark.parametrize("real_vals", [True, False])
+def test_spmm_matches_scipy(dv, r, real_vals):
+    rng = np.random.default_rng(r)
+    n = 1500
+    a = sp.random(n, n, density=0.01, random_state=rng, format="csc")
+    a = a + sp.diags_array(rng.standard_normal(n)).tocsc()
+    if not real_vals:
+        a = a + 1j * sp.random(n, n, density=0.005, random_state=rng, format="csc")
+    a = sp.csc_array(a)
+    q = crandn(rng, n, r)
+    at = dv.csr_of_transpose(a)
+    y = dv.spmm(at, dv.to_device_c128(q)).cpu().numpy()
+    ref = (q.T @ a).T          # the reference's q_t @ a, transposed
+    assert rel(y, ref) < 1e-13
+    # row-sliced operand (what a row-sharded rank holds)
+    lo, hi = 400, 1100
+    ys = dv.spmm(dv.csr_of_transpose(a, row_range=(lo, hi)), dv.to_device_c128(q)).cpu().numpy()
+    assert rel(ys, ref[lo:hi]) < 1e-13
+
+
+def test_spmm_empty_rows_and_long_rows(dv):
+    n, r = 300, 40
+    rng = np.random.default_rng(3)
+    dense = np.zeros((n, n))
+    dense[:, 7] = rng.standard_normal(n)        # a^T has one row with n entries (> 32: several fetch rounds)
+    dense[100, :50] = rng.standard_normal(50)
+    a = sp.csc_array(dense)
+    q = crandn(rng, n, r)
+    y = dv.spmm(dv.csr_of_transpose(a), dv.to_device_c128(q)).cpu().numpy()
+    assert rel(y, dense.T @ q) < 1e-13
+
+
+@pytest.mark.parametrize("conj", [False, True])
+def test_project_rhs(dv, conj):
+    from morfem_b200 import synthetic
+    rng = np.random.default_rng(1)
+    n, r = 900, 48
+    b = synthetic.port_matrix(n, 4, 19)
+    q = crandn(rng, n, r)
+    out = dv.project_rhs(dv.csc_to_device(b), dv.to_device_c128(q), 0, conj=conj).cpu().numpy()
+    ref = (q.conj().T if conj else q.T) @ b.toarray()
+    assert rel(out, ref) < 1e-14
+    # partial sums over two row shards add up to the full projection
+    bd = dv.csc_to_device(b)
+    p0 = dv.project_rhs(bd, dv.to_device_c128(q[:500]), 0, conj=conj).cpu().numpy()
+    p1 = dv.project_rhs(bd, dv.to_device_c128(q[500:]), 500, conj=conj).cpu().numpy()
+    assert rel(p0 + p1, ref) < 1e-14
