@@ -102,6 +102,8 @@ int mf_symmetrize_c128(const mf_c128* A, int64_t lda, int r, mf_c128* As, int64_
  * first exactly-zero pivot (LAPACK convention).  `variant`: 0 = auto, 1 = generic (one CTA per point),
  * 2 = register-panel kernel (r <= 128), 3 = blocked DMMA kernel.  ws from mf_sweep_ws_bytes. */
 size_t mf_sweep_ws_bytes(int r, int m, int64_t F, int variant);
+/* 1 when `variant` (1..3) can run this (r, m), else 0; variant 0 (auto) is always supported. */
+int mf_sweep_variant_supported(int r, int m, int variant);
 int mf_sweep_lu_gsm_c128(const mf_c128* A0, const mf_c128* A1, const mf_c128* A2, int64_t lda,
                          const mf_c128* Br, int64_t ldb, int r, int m,
                          const double* c0, const double* c1, const double* c2, const double* cb,

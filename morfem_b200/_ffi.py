@@ -40,6 +40,7 @@ SIGNATURES = {
                                     c_int, c_void_p, c_int64, c_void_p]),
     "mf_symmetrize_c128": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int64, c_void_p]),
     "mf_sweep_ws_bytes": (c_size_t, [c_int, c_int, c_int64, c_int]),
+    "mf_sweep_variant_supported": (c_int, [c_int, c_int, c_int]),
     "mf_sweep_lu_gsm_c128": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int,
                                      c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
                                      c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_size_t, c_void_p]),

@@ -24,6 +24,14 @@ static int pick_variant(int r, int m, int variant) {
     return 1;
 }
 
+extern "C" int mf_sweep_variant_supported(int r, int m, int variant) {
+    if (r <= 0 || r > 1024 || m <= 0 || m > MF_MAX_PORTS) return 0;
+    if (variant == 0 || variant == 1) return 1;
+    if (variant == 2) return sweep_regpanel_supports(r, m) ? 1 : 0;
+    if (variant == 3) return sweep_blocked_supports(r, m) ? 1 : 0;
+    return 0;
+}
+
 extern "C" size_t mf_sweep_ws_bytes(int r, int m, int64_t F, int variant) {
     if (r <= 0 || m <= 0 || F <= 0) return 256;
     size_t a = sweep_generic_ws_bytes(r, m, F);

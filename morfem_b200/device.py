@@ -48,7 +48,20 @@ def to_device_c128(a, device=None) -> torch.Tensor:
     """Host ndarray (real or complex) -> contiguous complex128 device tensor."""
     device = device or require_cuda()
     arr = np.ascontiguousarray(np.asarray(a), dtype=np.complex128)
-    return torch.from_numpy(arr).to(device, non_blocking=False)
+    return upload(arr, device)
+
+
+def real_or_complex_to_device(a, device=None) -> torch.Tensor:
+    """Host ndarray -> complex128 device tensor, copying only the bytes the host array has: a real float64 array
+    is uploaded as float64 (half the PCIe traffic) and widened on the device."""
+    device = device or require_cuda()
+    if isinstance(a, torch.Tensor):
+        t = a.to(device, non_blocking=True)
+        return t if t.dtype == C128 else t.to(C128)
+    arr = np.asarray(a)
+    if np.iscomplexobj(arr):
+        return to_device_c128(arr, device)
+    return upload(np.ascontiguousarray(arr, dtype=np.float64), device).to(C128)
 
 
 class _Workspaces:
@@ -72,6 +85,47 @@ class _Workspaces:
 workspaces = _Workspaces()
 
 
+class KernelTimer:
+    """Optional per-call CUDA-event timing of the C-ABI launches (bench.py's roofline leg).  Events are recorded
+    on the launching (current) stream around each call; ``summary()`` synchronises and aggregates by kernel name
+    with the ALGORITHMIC bytes and flops of each call (SURVEY.md section 8d formulas, restated in DESIGN.md)."""
+
+    def __init__(self):
+        self.records = []
+
+    def summary(self):
+        torch.cuda.synchronize()
+        agg = {}
+        for name, e0, e1, nbytes, flops in self.records:
+            a = agg.setdefault(name, {"calls": 0, "ms": 0.0, "bytes": 0.0, "flops": 0.0})
+            a["calls"] += 1
+            a["ms"] += e0.elapsed_time(e1)
+            a["bytes"] += nbytes
+            a["flops"] += flops
+        return agg
+
+
+timer: Optional[KernelTimer] = None
+
+
+class _timed:
+    def __init__(self, name, nbytes=0.0, flops=0.0):
+        self.name, self.nbytes, self.flops = name, float(nbytes), float(flops)
+
+    def __enter__(self):
+        if timer is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if timer is not None and exc[0] is None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            timer.records.append((self.name, self.e0, e1, self.nbytes, self.flops))
+        return False
+
+
 # ------------------------------------------------------------------------------------------ dense wrappers
 def gemm_tn(a: torch.Tensor, b: torch.Tensor, conj: bool = False, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """``op(a)^T b`` (ra x rb), reduction over the rows; ``conj`` selects ``a^H``."""
@@ -85,8 +139,10 @@ def gemm_tn(a: torch.Tensor, b: torch.Tensor, conj: bool = False, out: Optional[
         out = torch.empty((ra, rb), dtype=C128, device=a.device)
     nbytes = lib.mf_gemm_tn_ws_bytes(ra, rb, n)
     ws = workspaces.get("gemm_tn", nbytes, a.device)
-    _ffi.check(lib.mf_gemm_tn_c128(_ptr(a), a.stride(0), ra, _ptr(b), b.stride(0), rb, n, int(conj), _ptr(out), out.stride(0),
-                                   _ptr(ws), ws.numel(), _stream()), "mf_gemm_tn_c128")
+    same = a.data_ptr() == b.data_ptr() and ra == rb
+    with _timed("gemm_tn", nbytes=16.0 * n * (ra if same else ra + rb) + 16.0 * ra * rb, flops=8.0 * n * ra * rb):
+        _ffi.check(lib.mf_gemm_tn_c128(_ptr(a), a.stride(0), ra, _ptr(b), b.stride(0), rb, n, int(conj), _ptr(out), out.stride(0),
+                                       _ptr(ws), ws.numel(), _stream()), "mf_gemm_tn_c128")
     return out
 
 
@@ -100,8 +156,9 @@ def gemm_nn(a: torch.Tensor, w: torch.Tensor, out: Optional[torch.Tensor] = None
     rb = w.shape[1]
     if out is None:
         out = torch.empty((n, rb), dtype=C128, device=a.device)
-    _ffi.check(lib.mf_gemm_nn_c128(_ptr(a), a.stride(0), n, ra, _ptr(w), w.stride(0), rb, _ptr(out), out.stride(0), _stream()),
-               "mf_gemm_nn_c128")
+    with _timed("gemm_nn", nbytes=16.0 * n * (ra + rb) + 16.0 * ra * rb, flops=8.0 * n * ra * rb):
+        _ffi.check(lib.mf_gemm_nn_c128(_ptr(a), a.stride(0), n, ra, _ptr(w), w.stride(0), rb, _ptr(out), out.stride(0), _stream()),
+                   "mf_gemm_nn_c128")
     return out
 
 
@@ -136,9 +193,29 @@ class DeviceCSR:
         return self.vals.dtype == torch.float64
 
 
+# bytes moved over PCIe by the upload / download helpers (bench.py's e2e leg reads these)
+transfer_bytes = {"h2d": 0, "d2h": 0}
+
+
+def upload(arr: np.ndarray, device) -> torch.Tensor:
+    """One host->device copy of a contiguous ndarray (no dtype conversion, no intermediate host copy)."""
+    t = torch.from_numpy(arr)
+    transfer_bytes["h2d"] += t.numel() * t.element_size()
+    return t.to(device, non_blocking=False)
+
+
+def download(t: torch.Tensor, out: Optional[torch.Tensor] = None) -> np.ndarray:
+    """Device->host copy; ``out`` may be a pinned host tensor of the same shape/dtype."""
+    transfer_bytes["d2h"] += t.numel() * t.element_size()
+    if out is not None:
+        out.copy_(t, non_blocking=False)
+        return out.numpy()
+    return t.cpu().numpy()
+
+
 def csr_of_transpose(a_csc, device=None, row_range=None) -> DeviceCSR:
     """Upload the CSR view of ``a.T`` for a scipy ``csc_array``/``csc_matrix`` ``a`` (no conversion work: the
-    three CSC arrays are reused).  ``row_range=(lo, hi)`` uploads only rows lo..hi-1 of ``a.T``."""
+    three CSC arrays are reused as they are).  ``row_range=(lo, hi)`` uploads only rows lo..hi-1 of ``a.T``."""
     import scipy.sparse as sp
     device = device or require_cuda()
     a = a_csc if sp.issparse(a_csc) and a_csc.format == "csc" else sp.csc_array(a_csc)
@@ -148,12 +225,15 @@ def csr_of_transpose(a_csc, device=None, row_range=None) -> DeviceCSR:
     s, e = int(indptr[lo]), int(indptr[hi])
     if e - s >= 2 ** 31 or a.shape[0] >= 2 ** 31:
         raise ValueError("operator too large for int32 indices")
-    rowptr = (indptr[lo:hi + 1] - indptr[lo]).astype(np.int32)
-    colidx = np.asarray(a.indices[s:e], dtype=np.int32)
+    if lo == 0 and indptr.dtype == np.int32:
+        rowptr = indptr[:hi + 1]
+    else:
+        rowptr = (indptr[lo:hi + 1] - indptr[lo]).astype(np.int32)
+    colidx = np.ascontiguousarray(a.indices[s:e], dtype=np.int32)
     data = np.asarray(a.data[s:e])
     vals = np.ascontiguousarray(data, dtype=np.complex128 if np.iscomplexobj(data) else np.float64)
-    return DeviceCSR(torch.from_numpy(rowptr).to(device), torch.from_numpy(colidx).to(device),
-                     torch.from_numpy(vals).to(device), hi - lo, a.shape[0], lo)
+    return DeviceCSR(upload(np.ascontiguousarray(rowptr), device), upload(colidx, device), upload(vals, device),
+                     hi - lo, a.shape[0], lo)
 
 
 def spmm(a: DeviceCSR, q: torch.Tensor, out: Optional[torch.Tensor] = None, col_offset: int = 0) -> torch.Tensor:
@@ -164,8 +244,11 @@ def spmm(a: DeviceCSR, q: torch.Tensor, out: Optional[torch.Tensor] = None, col_
     if out is None:
         out = torch.empty((a.nrows, r), dtype=C128, device=q.device)
     colidx = a.colidx if col_offset == 0 else a.colidx - col_offset
-    _ffi.check(lib.mf_spmm_csr_c128(_ptr(a.rowptr), _ptr(colidx), _ptr(a.vals), int(a.is_real), a.nrows, _ptr(q), q.stride(0), r,
-                                    _ptr(out), out.stride(0), _stream()), "mf_spmm_csr_c128")
+    valb = 8.0 if a.is_real else 16.0
+    with _timed("spmm_csr", nbytes=a.nnz * (valb + 4.0) + 4.0 * (a.nrows + 1) + 16.0 * r * (a.nrows + q.shape[0]),
+                flops=(4.0 if a.is_real else 8.0) * a.nnz * r):
+        _ffi.check(lib.mf_spmm_csr_c128(_ptr(a.rowptr), _ptr(colidx), _ptr(a.vals), int(a.is_real), a.nrows, _ptr(q), q.stride(0), r,
+                                        _ptr(out), out.stride(0), _stream()), "mf_spmm_csr_c128")
     return out
 
 
@@ -188,9 +271,9 @@ def csc_to_device(b_csc, device=None) -> DeviceCSC:
     b = b_csc if sp.issparse(b_csc) and b_csc.format == "csc" else sp.csc_array(b_csc)
     data = np.asarray(b.data)
     vals = np.ascontiguousarray(data, dtype=np.complex128 if np.iscomplexobj(data) else np.float64)
-    return DeviceCSC(torch.from_numpy(np.asarray(b.indptr, dtype=np.int32)).to(device),
-                     torch.from_numpy(np.asarray(b.indices, dtype=np.int32)).to(device),
-                     torch.from_numpy(vals).to(device), b.shape[0], b.shape[1])
+    return DeviceCSC(upload(np.ascontiguousarray(b.indptr, dtype=np.int32), device),
+                     upload(np.ascontiguousarray(b.indices, dtype=np.int32), device),
+                     upload(vals, device), b.shape[0], b.shape[1])
 
 
 def project_rhs(b: DeviceCSC, q: torch.Tensor, row0: int = 0, conj: bool = False) -> torch.Tensor:
@@ -273,8 +356,9 @@ def orthonormalize(s: torch.Tensor, truncation_tol: float = 0.0, group=None, n_g
             sweeps = torch.zeros(1, dtype=torch.int32, device=dev)
             nbytes = lib.mf_jacobi_svd_ws_bytes(r)
             ws = workspaces.get("jacobi", nbytes, dev)
-            _ffi.check(lib.mf_jacobi_svd_c128(_ptr(r_tot), r_tot.stride(0), r, _ptr(u), u.stride(0), _ptr(sigma), 40, 4.0 * eps,
-                                              _ptr(sweeps), _ptr(ws), ws.numel(), _stream()), "mf_jacobi_svd_c128")
+            with _timed("jacobi_svd"):
+                _ffi.check(lib.mf_jacobi_svd_c128(_ptr(r_tot), r_tot.stride(0), r, _ptr(u), u.stride(0), _ptr(sigma), 40, 4.0 * eps,
+                                                  _ptr(sweeps), _ptr(ws), ws.numel(), _stream()), "mf_jacobi_svd_c128")
             sig = sigma.cpu().numpy()
             keep = r
             if truncation_tol > 0.0 and sig[0] > 0.0:
@@ -327,10 +411,13 @@ def sweep(a0s: Optional[torch.Tensor], a1s: Optional[torch.Tensor], a2s: Optiona
     info = torch.zeros(nf, dtype=torch.int32, device=dev)
     nbytes = lib.mf_sweep_ws_bytes(r, m, nf, variant)
     ws = workspaces.get("sweep", nbytes, dev)
-    _ffi.check(lib.mf_sweep_lu_gsm_c128(_ptr(a0s), _ptr(a1s), _ptr(a2s), lda, _ptr(br), br.stride(0), r, m,
-                                        _ptr(c0), _ptr(c1), _ptr(c2), _ptr(cb), _ptr(zscale), nf,
-                                        _ptr(x), _ptr(gsm), _ptr(info), variant, _ptr(ws), ws.numel(), _stream()),
-               "mf_sweep_lu_gsm_c128")
+    flops_pt = (8.0 / 3.0) * r ** 3 + 8.0 * r * r * m + 16.0 * r * r + 8.0 * r * m * m
+    bytes_pt = 16.0 * m * m * (gsm is not None) + 16.0 * r * m * (x is not None) + 40.0 + 4.0
+    with _timed("sweep_lu_gsm", nbytes=bytes_pt * nf, flops=flops_pt * nf):
+        _ffi.check(lib.mf_sweep_lu_gsm_c128(_ptr(a0s), _ptr(a1s), _ptr(a2s), lda, _ptr(br), br.stride(0), r, m,
+                                            _ptr(c0), _ptr(c1), _ptr(c2), _ptr(cb), _ptr(zscale), nf,
+                                            _ptr(x), _ptr(gsm), _ptr(info), variant, _ptr(ws), ws.numel(), _stream()),
+                   "mf_sweep_lu_gsm_c128")
     return SweepResult(x, gsm, info)
 
 

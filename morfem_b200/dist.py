@@ -1,0 +1,221 @@
+"""Multi-GPU partitioning of the reduced-order sweep path: one process per GPU, ``torch.distributed`` plumbing
+(NCCL over NVLink on the B200 box; the same code runs over ``gloo`` on CPU tensors in the world_size-2 tests).
+
+What shards and what is exchanged:
+
+  stage 1  rows of the snapshot block are block-sharded; each rank forms an r x r partial Gram matrix, the
+           partials are summed with ONE all-reduce per Cholesky-QR pass; the r x r factorisations are replicated
+           (deterministic kernels on identical input -> identical factors on every rank, no broadcast needed);
+  stage 2  operator rows are sharded conformally with Q; the SpMM needs the Q rows its column indices reach
+           outside the local block -- a halo window exchanged point-to-point with the owning ranks (banded FEM
+           ordering keeps it a few hundred rows); r x r partial projections are all-reduced;
+  stage 3/4 sweep points are split into contiguous blocks, no communication; the F x M x M S-parameters are
+           collected with an all-gather.
+
+This module holds the partition arithmetic and the communication steps (device agnostic); the compute between
+them is morfem_b200.device (CUDA only, no fallback) -- see ``ShardedHotPath``.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import List, Optional, Tuple
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+# ------------------------------------------------------------------------------------- partition arithmetic
+def even_split(total: int, world: int, rank: int) -> Tuple[int, int]:
+    """Contiguous block ``[lo, hi)`` of ``total`` items for ``rank``; the first ``total % world`` ranks get one more."""
+    if world <= 0 or not (0 <= rank < world):
+        raise ValueError("even_split: need 0 <= rank < world")
+    base, extra = divmod(int(total), world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def owner_ranges(total: int, world: int) -> List[Tuple[int, int]]:
+    return [even_split(total, world, r) for r in range(world)]
+
+
+def column_window(indptr: np.ndarray, indices: np.ndarray, lo: int, hi: int, ncols: int) -> Tuple[int, int]:
+    """Smallest contiguous range of column indices touched by CSR rows ``lo..hi-1`` (the halo window of the SpMM),
+    always containing ``[lo, hi)`` itself clipped to ``ncols`` so that the local block sits inside the window."""
+    s, e = int(indptr[lo]), int(indptr[hi])
+    w0, w1 = min(lo, ncols), min(hi, ncols)
+    if e > s:
+        cols = indices[s:e]
+        w0, w1 = min(w0, int(cols.min())), max(w1, int(cols.max()) + 1)
+    return w0, w1
+
+
+@dataclass
+class HaloPlan:
+    """Which Q rows this rank receives from / sends to every peer for one window ``[win0, win1)``."""
+    rank: int
+    world: int
+    row0: int
+    row1: int
+    win0: int
+    win1: int
+    recv: List[Tuple[int, int, int]] = field(default_factory=list)   # (peer, global_lo, global_hi) rows received from peer
+    send: List[Tuple[int, int, int]] = field(default_factory=list)   # (peer, global_lo, global_hi) rows sent to peer
+
+    @property
+    def halo_rows(self) -> int:
+        return sum(hi - lo for _, lo, hi in self.recv)
+
+
+def build_halo_plan(rank: int, world: int, n_rows: int, windows: List[Tuple[int, int]]) -> HaloPlan:
+    """``windows[p]`` is rank p's column window; ownership is ``even_split(n_rows, world, p)``."""
+    owned = owner_ranges(n_rows, world)
+    row0, row1 = owned[rank]
+    win0, win1 = windows[rank]
+    plan = HaloPlan(rank, world, row0, row1, win0, win1)
+    for p in range(world):
+        if p == rank:
+            continue
+        lo, hi = max(win0, owned[p][0]), min(win1, owned[p][1])
+        if hi > lo:
+            plan.recv.append((p, lo, hi))
+        lo, hi = max(windows[p][0], row0), min(windows[p][1], row1)
+        if hi > lo:
+            plan.send.append((p, lo, hi))
+    return plan
+
+
+def gather_windows(window: Tuple[int, int], group=None) -> List[Tuple[int, int]]:
+    """All ranks' windows (plan time, host integers)."""
+    world = dist.get_world_size(group)
+    out: List[Optional[Tuple[int, int]]] = [None] * world
+    dist.all_gather_object(out, (int(window[0]), int(window[1])), group=group)
+    return [tuple(w) for w in out]
+
+
+# ------------------------------------------------------------------------------------------ communication
+def _as_real(t: torch.Tensor) -> torch.Tensor:
+    return torch.view_as_real(t) if t.is_complex() else t
+
+
+def allreduce_sum_(t: torch.Tensor, group=None) -> torch.Tensor:
+    """In-place sum over ranks of a (complex) tensor: the r x r Gram / projection partials."""
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(_as_real(t), op=dist.ReduceOp.SUM, group=group)
+    return t
+
+
+def exchange_halo(q_local: torch.Tensor, plan: HaloPlan, out: Optional[torch.Tensor] = None, group=None) -> torch.Tensor:
+    """Assemble rows ``[win0, win1)`` of the global Q on this rank: the local block is copied, the rest is
+    received straight into its slot of the window buffer from the owning ranks (point to point, one message per
+    peer and direction)."""
+    r = q_local.shape[1]
+    nwin = plan.win1 - plan.win0
+    if out is None or out.shape[0] < nwin or out.shape[1] != r:
+        out = torch.empty((nwin, r), dtype=q_local.dtype, device=q_local.device)
+    win = out[:nwin]
+    win[plan.row0 - plan.win0:plan.row1 - plan.win0].copy_(q_local)
+    ops = []
+    for peer, lo, hi in plan.send:
+        ops.append(dist.P2POp(dist.isend, _as_real(q_local[lo - plan.row0:hi - plan.row0]), peer, group=group))
+    for peer, lo, hi in plan.recv:
+        ops.append(dist.P2POp(dist.irecv, _as_real(win[lo - plan.win0:hi - plan.win0]), peer, group=group))
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+    return win
+
+
+def gather_points(local: torch.Tensor, f_total: int, group=None) -> torch.Tensor:
+    """All-gather of per-point results split with ``even_split``: returns the (f_total, ...) tensor on every rank."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return local
+    world = dist.get_world_size(group)
+    counts = [hi - lo for lo, hi in owner_ranges(f_total, world)]
+    cmax = max(counts)
+    tail = tuple(local.shape[1:])
+    padded = torch.zeros((cmax,) + tail, dtype=local.dtype, device=local.device)
+    padded[:local.shape[0]].copy_(local)
+    gathered = torch.empty((world * cmax,) + tail, dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(_as_real(gathered), _as_real(padded), group=group)
+    if all(c == cmax for c in counts):
+        return gathered
+    return torch.cat([gathered[p * cmax:p * cmax + counts[p]] for p in range(world)], dim=0)
+
+
+# -------------------------------------------------------------------------------------------- sharded path
+class ShardedHotPath:
+    """Stages 1-4 for one rank of a row-/point-sharded job.  Inputs are this rank's slices, already on its GPU:
+
+      operators   list of three scipy csc arrays (GLOBAL; only the local CSR rows of ``a^T`` are uploaded) or None
+      b           scipy csc port matrix (global, tiny)
+      coefficient arrays c0, c1, c2, cb, zscale for the LOCAL sweep points (host ndarrays)
+    """
+
+    def __init__(self, operators, b, n_rows: int, f_total: int, coeffs_global, group=None):
+        from . import device as dv
+        self.dv = dv
+        self.group = group if group is not None else (dist.group.WORLD if dist.is_initialized() else None)
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.dev = dv.require_cuda()
+        self.n_rows = n_rows
+        self.row0, self.row1 = even_split(n_rows, self.world, self.rank)
+        self.f_total = f_total
+        self.f0, self.f1 = even_split(f_total, self.world, self.rank)
+        self.ops = []
+        self.plans = []
+        for a in operators:
+            if a is None or a.nnz == 0:
+                self.ops.append(None)
+                self.plans.append(None)
+                continue
+            window = column_window(np.asarray(a.indptr), np.asarray(a.indices), self.row0, self.row1, a.shape[0])
+            windows = gather_windows(window, group) if self.world > 1 else [window]
+            plan = build_halo_plan(self.rank, self.world, n_rows, windows)
+            csr = dv.csr_of_transpose(a, self.dev, row_range=(self.row0, self.row1))
+            if plan.win0:
+                csr.colidx = csr.colidx - plan.win0          # window-relative column indices, computed once
+            self.ops.append(csr)
+            self.plans.append(plan)
+        self.b = dv.csc_to_device(b, self.dev)
+        self.coeffs = [dv.upload(np.ascontiguousarray(c[self.f0:self.f1], dtype=np.float64), self.dev) for c in coeffs_global]
+        self._win = None
+        self.stage_events = None     # bench.py: set to a list to collect per-stage CUDA events
+
+    def _mark(self, ev):
+        if ev is not None:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            ev.append(e)
+
+    def step(self, s_local: torch.Tensor, want_x: bool = False, gather: bool = True):
+        """One pass of the hot path.  Returns (gsm_all or gsm_local, q_local, (a0_r, a1_r, a2_r, b_r), sweep result)."""
+        dv = self.dv
+        group = self.group if self.world > 1 else None
+        ev = [] if self.stage_events is not None else None
+        self._mark(ev)
+        q, info = dv.orthonormalize(s_local, group=group)
+        self._mark(ev)
+        reduced = []
+        for csr, plan in zip(self.ops, self.plans):
+            if csr is None:
+                reduced.append(None)
+                continue
+            if self.world > 1:
+                self._win = exchange_halo(q, plan, self._win, group)
+                y = dv.spmm(csr, self._win[:plan.win1 - plan.win0])
+            else:
+                y = dv.spmm(csr, q)
+            reduced.append(allreduce_sum_(dv.gemm_tn(y, q, conj=False), group))
+        b_r = allreduce_sum_(dv.project_rhs(self.b, q, self.row0, conj=False), group)
+        sym = [None if o is None else dv.symmetrize(o) for o in reduced]
+        c0, c1, c2, cb, zs = self.coeffs
+        self._mark(ev)
+        res = dv.sweep(sym[0], sym[1], sym[2], b_r, c0, c1, c2, cb, zs, want_x=want_x, want_gsm=True)
+        self._mark(ev)
+        gsm = gather_points(res.gsm, self.f_total, group) if (gather and self.world > 1) else res.gsm
+        self._mark(ev)
+        if ev is not None:
+            self.stage_events.append(ev)
+        return gsm, q, (reduced[0], reduced[1], reduced[2], b_r), res

@@ -163,7 +163,7 @@ def _sweep_device(domain, ops_r, b_r, t_a0, t_a1, t_a2, t_b, want_x=True, want_g
     domain = np.asarray(domain, dtype=np.float64)
     coeffs = [coefficient_array(f, domain) for f in (t_a0, t_a1, t_a2, t_b)]
     zs = 2 * pi * domain * epsilon_0
-    c0, c1, c2, cb, zsd = (torch.from_numpy(np.ascontiguousarray(c)).to(dev) for c in (*coeffs, zs))
+    c0, c1, c2, cb, zsd = (dv.upload(np.ascontiguousarray(c, dtype=np.float64), dev) for c in (*coeffs, zs))
     sym = [None if o is None else dv.symmetrize(o) for o in ops_r]
     return dv.sweep(sym[0], sym[1], sym[2], b_r, c0, c1, c2, cb, zsd, want_x=want_x, want_gsm=want_gsm, variant=variant)
 
@@ -274,6 +274,33 @@ def projection_base(md: ModelDefinition, _return_device: bool = False):
         stacked = torch.cat((qd, dv.to_device_c128(q_new)), dim=1).contiguous()
         qd, _ = dv.orthonormalize(stacked, truncation_tol=TRUNCATION_TOL)
     return qd if _return_device else _basis_to_host(qd, md)
+
+
+def morfem_from_snapshots(snapshots: np.ndarray, domain: np.ndarray, a0: csc_array, a1: csc_array, a2: csc_array, b: csc_array,
+                          t_a0: Callable[[float], float] = lambda t: 1.,
+                          t_a1: Callable[[float], float] = lambda t: t,
+                          t_a2: Callable[[float], float] = lambda t: t ** 2,
+                          t_b: Callable[[float], float] = lambda t: t):
+    """The four hot stages on a GIVEN snapshot block (N x r): ``q = svd(snapshots)[0]`` (implementation.py:226/298/210),
+    then lines :178-186 verbatim.  Same 6-tuple as ``morfem``; this is ``morfem`` minus the greedy point selection and
+    its full-order SuperLU solves, i.e. exactly the path the north star puts on the GPU."""
+    from . import device as dv
+    md = ModelDefinition(domain, a0, a1, a2, b, t_a0, t_a1, t_a2, t_b)
+    qd, _ = dv.orthonormalize(dv.real_or_complex_to_device(snapshots), truncation_tol=TRUNCATION_TOL)
+    ops = _DeviceOperators(md)
+    a0_r, a1_r, a2_r, b_r = ops.project(qd)
+    res = _sweep_device(domain, [a0_r, a1_r, a2_r], b_r, t_a0, t_a1, t_a2, t_b, want_x=True, want_gsm=False)
+    _warn_singular(res.info.cpu().numpy())
+    real = _real_inputs(a0, a1, a2, b) and not np.iscomplexobj(snapshots)
+    r = qd.shape[1]
+
+    def host(t):
+        if t is None:
+            return np.zeros((r, r)) if real else np.zeros((r, r), dtype=complex)
+        arr = t.cpu().numpy()
+        return np.ascontiguousarray(arr.real) if real else arr
+
+    return host(res.x), host(qd), host(a0_r), host(a1_r), host(a2_r), host(b_r)
 
 
 def morfem(domain: np.ndarray, a0: csc_array, a1: csc_array, a2: csc_array, b: csc_array,

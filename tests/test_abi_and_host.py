@@ -1,0 +1,104 @@
+"""CPU-side checks: the C-ABI library loads and exports exactly what include/morfem_b200.h declares, argument
+validation answers without touching a GPU, and the host-side helpers mirror the reference's behaviour."""
+import ctypes
+import math
+import os
+import re
+import warnings
+
+import numpy as np
+import pytest
+from scipy.sparse import csc_array
+
+from morfem_b200 import _ffi, implementation as impl, test_helpers as th, synthetic
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_functions():
+    text = open(os.path.join(ROOT, "include", "morfem_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(mf_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_library_and_binding_agree():
+    names = header_functions()
+    assert len(names) >= 20
+    assert sorted(_ffi.SIGNATURES) == names
+    lib = _ffi.load()
+    for n in names:
+        assert hasattr(lib, n), n
+    assert lib.mf_version() == 100
+
+
+def test_argument_validation_without_gpu():
+    lib = _ffi.load()
+    # NULL operands: every entry point must answer with -(argument index) and a message, never crash
+    st = lib.mf_gemm_tn_c128(None, 4, 4, None, 4, 4, 10, 0, None, 4, None, 0, None)
+    assert st == -1 and b"mf_gemm_tn_c128" in lib.mf_last_error()
+    st = lib.mf_spmm_csr_c128(None, None, None, 1, 10, None, 4, 4, None, 4, None)
+    assert st == -1
+    st = lib.mf_sweep_lu_gsm_c128(None, None, None, 8, None, 2, 8, 2, None, None, None, None, None, 4, None, None, None, 0,
+                                  None, 0, None)
+    assert st == -1
+    with pytest.raises(_ffi.MorfemB200Error):
+        _ffi.check(st, "mf_sweep_lu_gsm_c128")
+    assert lib.mf_gemm_tn_ws_bytes(64, 64, 100000) >= 64 * 64 * 16
+    assert lib.mf_jacobi_svd_ws_bytes(64) > 2 * 64 * 64 * 16
+
+
+def test_product_path_refuses_to_run_without_cuda():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    a0, a1, a2, b = synthetic.reduced_model(8, 2, seed=0)
+    md = impl.ModelDefinition(np.linspace(3e9, 5e9, 4), a0, a1, a2, b, lambda t: 1.0, lambda t: t, lambda t: t ** 2, th.b_coefficient)
+    with pytest.raises(_ffi.MorfemB200Error):
+        impl.solve_finite_element_method(md)      # no CPU fallback on the hot path
+
+
+def test_coefficient_array_vectorised_and_scalar_fallback():
+    dom = np.linspace(3e9, 5e9, 17)
+    assert np.array_equal(impl.coefficient_array(lambda t: t ** 2, dom), dom ** 2)
+    assert np.array_equal(impl.coefficient_array(lambda t: 1.0, dom), np.ones(17))
+    cb = impl.coefficient_array(th.b_coefficient, dom)            # math.sqrt: scalar-only callable
+    assert np.array_equal(cb, np.array([th.b_coefficient(t) for t in dom]))
+    with pytest.raises(ValueError):
+        impl.coefficient_array(th.b_coefficient, np.array([1e9, 3e9]))   # below cutoff: the reference's ValueError
+    # a callable whose vectorised form is *different* from its scalar form must fall back to scalar evaluation
+    odd = lambda t: float(np.sum(t))  # noqa: E731
+    assert np.array_equal(impl.coefficient_array(odd, dom), dom)
+
+
+def test_host_helpers_match_reference_semantics():
+    rng = np.random.default_rng(0)
+    a = rng.standard_normal((5, 5))
+    md = impl.ModelDefinition(np.array([2.0]), a, 2 * a, 3 * a, rng.standard_normal((5, 2)), lambda t: 1.0, lambda t: t,
+                              lambda t: t ** 2, lambda t: t)
+    s = impl.system_matrix(2.0, md)
+    full = a + 2.0 * 2 * a + 4.0 * 3 * a
+    assert np.allclose(s, (full + full.T) / 2)
+    assert np.allclose(impl.impulse_vector(2.0, md), 2.0 * md.b)
+    with pytest.raises(Exception):
+        impl.h(np.zeros(3))
+    z = rng.standard_normal((3, 2)) + 1j * rng.standard_normal((3, 2))
+    assert np.array_equal(impl.h(z), z.conj().T)
+    assert th.b_coefficient(4e9) == math.sqrt(math.sqrt(((2 * math.pi * 4e9) / 299792458.0) ** 2 - 54.5976295582387 ** 2) / 4e9)
+    pts = th.equally_distributed_points(np.arange(10), 4)
+    assert list(pts) == [0, 3, 6, 9]
+    with pytest.raises(Exception):
+        th.equally_distributed_points(np.arange(3), 4)
+
+
+def test_full_order_branch_stays_on_scipy():
+    """solve_fem_point on sparse operators is the SuperLU call of implementation.py:475 (outside the hot path)."""
+    ct, tt = synthetic.waveguide_operators(3, 2, 6)
+    wp = synthetic.port_matrix(ct.shape[0], 2, 5)
+    in_c, in_gamma, in_b = synthetic.driver_scaled(ct, tt, wp)
+    md = impl.ModelDefinition(np.array([4e9]), in_c, csc_array(in_c.shape), in_gamma, in_b, lambda t: 1.0, lambda t: t,
+                              lambda t: t ** 2, th.b_coefficient)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        x = impl.solve_fem_point(4e9, md)
+    a = in_c + (4e9) ** 2 * in_gamma
+    assert np.allclose(a @ x, th.b_coefficient(4e9) * in_b.toarray(), atol=1e-9 * np.abs(in_b.toarray()).max())
