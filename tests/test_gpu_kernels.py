@@ -100,7 +100,7 @@ def test_jacobi_svd(dv, r, cmplx):
     uh, sh = u.cpu().numpy(), sigma.cpu().numpy()
     u_ref, s_ref, _ = np.linalg.svd(m)
     assert np.all(np.diff(sh) <= 0)
-    assert np.max(np.abs(sh - s_ref) / s_ref) < 1e-12
+    assert np.max(np.abs(sh - s_ref)) < 1e-13 * s_ref[0]       # gesdd itself resolves sigma only to eps * sigma_max
     assert rel(uh.conj().T @ uh, np.eye(r)) < 1e-13
     # U^H M must have orthogonal rows with norms sigma
     t = uh.conj().T @ m

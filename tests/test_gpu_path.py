@@ -67,8 +67,10 @@ def test_orthonormalize_live_reference_svd_pair(dv):
     q = qd.cpu().numpy().real
     keep = int(np.count_nonzero(info.sigma > 1e-10 * info.sigma[0]))
     assert keep >= 4
-    assert orc.subspace_residual(g["svd_out"][:, :keep], q[:, :keep]) < 1e-9
-    assert max(np.max(orc.principal_angles(g["svd_out"][:, :keep], q[:, :keep])), 0.0) < 1e-6
+    gap = info.sigma[keep - 1] - (info.sigma[keep] if keep < s.shape[1] else 0.0)
+    tol = max(1e-10, 1e3 * np.finfo(float).eps * info.sigma[0] / gap)
+    assert orc.subspace_residual(g["svd_out"][:, :keep], q[:, :keep]) < tol
+    assert np.max(orc.principal_angles(g["svd_out"][:, :keep], q[:, :keep])) < max(1e-6, tol)
 
 
 def test_orthonormalize_truncation(dv):
@@ -125,15 +127,20 @@ def test_chained_path_stages_fixture(dv):
     qd, info = dv.orthonormalize(dv.to_device_c128(g["snapshots"][:, :keep]))
     q = qd.cpu().numpy().real
     q_ref = orc.orthonormal_basis(g["snapshots"][:, :keep])
-    assert orc.subspace_residual(q_ref, q) < 1e-9
+    # any rounding-level perturbation of S moves span(S) by eps * cond(S) (cond ~ 7e8 for these true snapshots)
+    span_tol = max(1e-10, 50 * np.finfo(float).eps * info.sigma[0] / info.sigma[-1])
+    assert orc.subspace_residual(q_ref, q) < span_tol
     md = impl.ModelDefinition(g["f"], in_c, csc_array(in_c.shape), in_gamma, in_b, lambda t: 1.0, lambda t: t, lambda t: t ** 2,
                               th.b_coefficient)
     ops = impl._DeviceOperators(md)
     a0_r, a1_r, a2_r, b_r = ops.project(qd)
     ref = orc.galerkin_projection(q_ref, in_c, md.a1, in_gamma, in_b)
     # reduced matrices: express the reference's in the new basis
-    assert orc.rel_err(a0_r.cpu().numpy().real, orc.align_reduced(ref[0], q_ref, q)) < 1e-10
-    assert orc.rel_err(a2_r.cpu().numpy().real, orc.align_reduced(ref[2], q_ref, q)) < 1e-10
+    assert orc.rel_err(a0_r.cpu().numpy().real, orc.align_reduced(ref[0], q_ref, q)) < max(1e-10, 10 * span_tol)
+    assert orc.rel_err(a2_r.cpu().numpy().real, orc.align_reduced(ref[2], q_ref, q)) < max(1e-10, 10 * span_tol)
+    # stage isolated (the device's own q on both sides): the north star's 1e-10 on reduced matrices
+    iso = orc.galerkin_projection(q, in_c, md.a1, in_gamma, in_b)
+    assert orc.rel_err(a0_r.cpu().numpy().real, iso[0]) < 1e-10 and orc.rel_err(a2_r.cpu().numpy().real, iso[2]) < 1e-10
     res = impl._sweep_device(g["f"], [a0_r, a1_r, a2_r], b_r, md.t_a0, md.t_a1, md.t_a2, md.t_b, want_x=True, want_gsm=True)
     x_ref = orc.reduced_sweep(g["f"], *ref, md.t_a0, md.t_a1, md.t_a2, md.t_b)
     s_ref = orc.scattering_sweep(g["f"], x_ref, ref[3])
