@@ -19,8 +19,8 @@ extern "C" int64_t mf_launch_count(void) { return (int64_t)g_mf_launches.load(st
 
 static int pick_variant(int r, int m, int variant) {
     if (variant != 0) return variant;
+    if (sweep_blocked_supports(r, m)) return 3;      // measured faster than the register-panel kernel for every r it supports
     if (sweep_regpanel_supports(r, m)) return 2;
-    if (sweep_blocked_supports(r, m)) return 3;
     return 1;
 }
 
