@@ -9,12 +9,15 @@
 //
 // Per panel of 8 columns (LAPACK getrf order; implementation.py:477 `lu_factor`):
 //   A. ONE warp factors the (R - 8k) x 8 panel in registers, one (or a few) rows per lane.  Partial pivoting uses
-//      LAPACK's izamax magnitude |re| + |im| with first-maximum tie breaking, evaluated with three warp REDUX
-//      operations (high word, low word, position) -- no CTA barrier inside the panel.  Row exchanges are tracked as
-//      positions and materialise when the panel is written back.
+//      LAPACK's izamax magnitude |re| + |im| with first-maximum tie breaking, evaluated with warp REDUX/VOTE
+//      operations (high word; low word and position only on ties) -- no CTA barrier inside the panel.  Row exchanges
+//      are tracked as positions and materialise when the panel is written back.
 //   B. one thread per trailing column applies the 8 row exchanges and the unit-lower triangular solve U12 = L11^-1 A12.
-//   C. all warps: A22 -= L21 U12 as complex DMMA.8x8x4 block products (4 real DMMAs per complex k-step), fragments
-//      loaded straight from the swizzled matrix.
+//   C. A22 -= L21 U12 as complex DMMA.8x8x4 block products (4 real DMMAs per complex k-step), fragments loaded
+//      straight from the swizzled matrix.
+// Schedule (look-ahead): ONE CTA barrier per panel.  After the barrier that publishes panel k, warp 0 alone applies
+// B + C to column block k+1 and immediately factors panel k+1 (the critical path), while the other warps apply
+// B + C of step k to all remaining column blocks in its shadow.
 // The right-hand sides ride along as extra column blocks, so L is never needed again; back substitution
 // (`lu_solve`, implementation.py:478) and the S-parameter algebra (test_helpers.py:9-14) form the epilogue.
 // Roofline: FP64 pipe.  Operators are L2 resident; per point the kernel writes 16 m^2 bytes (+ 16 r m with X).
@@ -29,7 +32,7 @@ __device__ __forceinline__ int swz(int g) { return (((g ^ (g >> 2)) & 1) << 2) |
 __device__ __forceinline__ int mphys(int row, int col, int LD) { return row * LD + (col & ~7) + ((col & 7) ^ swz(row & 7)); }
 
 // 1/a by Smith's formula with reciprocals (two correctly rounded reciprocals instead of three divisions)
-__device__ __forceinline__ cplx crecip2(cplx a) {
+__device__ __noinline__ cplx crecip2(cplx a) {
     if (fabs(a.x) >= fabs(a.y)) {
         const double ia = 1.0 / a.x, t = a.y * ia, d = fma(a.y, t, a.x), id = 1.0 / d;
         return cmake(id, -t * id);
@@ -40,139 +43,201 @@ __device__ __forceinline__ cplx crecip2(cplx a) {
 }
 
 // ---- A. panel factorisation by one warp -------------------------------------------------------------------
-// Rows row0 .. R-1, columns row0 .. row0+7.  On exit the panel holds (at the exchanged row positions) -L11 \ U11 with
-// the RECIPROCAL of each pivot on the diagonal, and -L21 below (multipliers are stored NEGATED so that the trailing
-// update and the triangular solve are pure multiply-adds); piv[j] = position the j-th pivot row came from.
-// `urow` is a 2 x 8 element shared staging buffer for the pivot row (double buffered over the column index).
+// Rows row0 .. R-1, columns row0 .. row0+7, one (or a few) rows per lane, held in registers.  On exit the panel holds
+// (at the exchanged row positions) -L11 \ U11 with the RECIPROCAL of each pivot on the diagonal, and -L21 below
+// (multipliers are stored NEGATED so that the trailing update and the triangular solve are pure multiply-adds);
+// piv[j] = position the j-th pivot row came from.
+// Per column: every lane forms the magnitude of its best candidate and -- speculatively, overlapping the latency of
+// the warp reduction -- its reciprocal; the winning lane publishes its finished row (L11 part, reciprocal pivot, U
+// part) straight into the row's final place in shared memory and retires the slot; after one __syncwarp the other
+// lanes read reciprocal and U entries from there.  `pbuf` = two ints for the pivot position (double buffered).
 template <int SLOTS>
 __device__ __forceinline__ void panel_factor(cplx* M, const int LD, const int R, const int row0, const int lane,
-                                             cplx* urow, int* piv, int* info_sh) {
-    double ar[SLOTS][8], ai[SLOTS][8];
+                                             int* pbuf, int* piv, int* info_sh) {
+    cplx a[SLOTS][8];
     int pos[SLOTS];
-    unsigned act = 0;                       // bit s: slot s holds a real row that has not been a pivot yet
-    unsigned valid = 0;
+    bool act[SLOTS];                        // slot holds a real row that has not been a pivot yet
 #pragma unroll
     for (int s = 0; s < SLOTS; ++s) {
         const int row = row0 + lane + 32 * s;
         pos[s] = row;
-        const bool v = row < R;
-        if (v) valid |= 1u << s;
+        act[s] = row < R;
         const int sw = swz(row & 7);
         const cplx* src = M + row * LD + row0;
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            cplx x = cmake(0.0, 0.0);
-            if (v) x = src[c ^ sw];
-            ar[s][c] = x.x; ai[s][c] = x.y;
-        }
+        for (int c = 0; c < 8; ++c) a[s][c] = act[s] ? src[c ^ sw] : cmake(0.0, 0.0);
     }
-    act = valid;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-        // this lane's best candidate: (magnitude descending, position ascending)
-        unsigned long long bk = 0ull; int bp = 0x7fffffff, bs = 0;
+        const int T = row0 + j;
+        // this lane's best candidate: (magnitude descending, position ascending); retired slots count as -1
+        double vb = act[0] ? fabs(a[0][j].x) + fabs(a[0][j].y) : -1.0;
+        int pbest = pos[0], bs = 0;
+        cplx cand = a[0][j];
 #pragma unroll
-        for (int s = 0; s < SLOTS; ++s) {
-            const double v = fabs(ar[s][j]) + fabs(ai[s][j]);
-            const unsigned long long key = ((act >> s) & 1u) ? ((unsigned long long)__double_as_longlong(v) + (1ull << 32)) : 0ull;
-            const bool better = (key > bk) || (key == bk && pos[s] < bp);
-            if (better) { bk = key; bp = pos[s]; bs = s; }
+        for (int s = 1; s < SLOTS; ++s) {
+            const double v = act[s] ? fabs(a[s][j].x) + fabs(a[s][j].y) : -1.0;
+            if (v > vb || (v == vb && pos[s] < pbest)) { vb = v; pbest = pos[s]; bs = s; cand = a[s][j]; }
         }
-        const unsigned bh = (unsigned)(bk >> 32), bl = (unsigned)bk;
-        const unsigned hmax = __reduce_max_sync(FULL, bh);
-        const bool c1 = (bh == hmax);
-        const unsigned lmax = __reduce_max_sync(FULL, c1 ? bl : 0u);
-        const bool c2 = c1 && (bl == lmax);
-        const int P = __reduce_min_sync(FULL, c2 ? bp : 0x7fffffff);
-        const bool own = c2 && (bp == P);
-        // pivot row, columns j..7, through shared memory
-        cplx* ub = urow + 8 * (j & 1);
+        // speculative reciprocal of this lane's candidate
+        cplx rc = cmake(0.0, 0.0);
+        if (vb > 0.0) rc = (cand.y == 0.0) ? cmake(1.0 / cand.x, 0.0) : crecip2(cand);
+        // warp arg-max: high word first, low word and position only when needed
+        const int hi = __double2hiint(vb);
+        const int hmax = __reduce_max_sync(FULL, hi);
+        bool own = (hi == hmax);
+        if (__popc(__ballot_sync(FULL, own)) != 1) {
+            const unsigned lo = (unsigned)__double2loint(vb);
+            const unsigned lmax = __reduce_max_sync(FULL, own ? lo : 0u);
+            own = own && (lo == lmax);
+            if (__popc(__ballot_sync(FULL, own)) != 1) {       // exact tie: lowest position wins (first maximum, as izamax)
+                const int pmin = __reduce_min_sync(FULL, own ? pbest : 0x7fffffff);
+                own = own && (pbest == pmin);
+            }
+        }
+        cplx* prow = M + T * LD + row0;     // final place of the pivot row; (T & 7) == j
         if (own) {
+            pbuf[j & 1] = pbest;
+            piv[j] = pbest;
+            if (!(vb > 0.0) && *info_sh == 0) *info_sh = T + 1;   // exactly zero pivot (LAPACK info)
 #pragma unroll
             for (int s = 0; s < SLOTS; ++s)
                 if (s == bs) {
 #pragma unroll
-                    for (int c = j; c < 8; ++c) ub[c] = cmake(ar[s][c], ai[s][c]);
+                    for (int c = 0; c < 8; ++c) prow[c ^ swz(j)] = (c == j) ? rc : a[s][c];
+                    act[s] = false;
                 }
         }
         __syncwarp();
-        double ur[8], ui[8];
+        const int P = *reinterpret_cast<volatile int*>(pbuf + (j & 1));
+        const unsigned prow_s = (unsigned)__cvta_generic_to_shared(prow);
+        cplx rcp, u[8];
+        asm volatile("ld.volatile.shared.v2.f64 {%0, %1}, [%2];" : "=d"(rcp.x), "=d"(rcp.y) : "r"(prow_s + 16u * (j ^ swz(j))));
 #pragma unroll
-        for (int c = j; c < 8; ++c) {       // written by another lane: volatile keeps the loads after the barrier
-            const volatile double* up = reinterpret_cast<const volatile double*>(ub + c);
-            ur[c] = up[0]; ui[c] = up[1];
-        }
-        const bool zero = (hmax == 1u && lmax == 0u);          // pivot magnitude is exactly +0.0
-        cplx rcp;
-        if (zero) rcp = cmake(0.0, 0.0);
-        else if (ui[j] == 0.0) rcp = cmake(1.0 / ur[j], 0.0);  // real pivot (the reference's data is real): one reciprocal
-        else rcp = crecip2(cmake(ur[j], ui[j]));
-        const int T = row0 + j;
-        if (lane == 0) { piv[j] = P; if (zero && *info_sh == 0) *info_sh = T + 1; }
+        for (int c = j + 1; c < 8; ++c)
+            asm volatile("ld.volatile.shared.v2.f64 {%0, %1}, [%2];" : "=d"(u[c].x), "=d"(u[c].y) : "r"(prow_s + 16u * (c ^ swz(j))));
 #pragma unroll
         for (int s = 0; s < SLOTS; ++s) {
-            const bool mine = own && (s == bs);
-            const bool elim = ((act >> s) & 1u) && !mine;
-            // negated multiplier; exactly zero for rows that do not take part (finished pivot rows, padding slots)
-            const double nlx = elim ? -(ar[s][j] * rcp.x - ai[s][j] * rcp.y) : 0.0;
-            const double nly = elim ? -(ar[s][j] * rcp.y + ai[s][j] * rcp.x) : 0.0;
-            ar[s][j] = mine ? rcp.x : (elim ? nlx : ar[s][j]);
-            ai[s][j] = mine ? rcp.y : (elim ? nly : ai[s][j]);
+            // negated multiplier (retired slots compute on stale values that are never used again)
+            const cplx nl = cmake(-(a[s][j].x * rcp.x - a[s][j].y * rcp.y), -(a[s][j].x * rcp.y + a[s][j].y * rcp.x));
+            a[s][j] = nl;
 #pragma unroll
-            for (int c = j + 1; c < 8; ++c) {
-                ar[s][c] = fma(nlx, ur[c], ar[s][c]); ar[s][c] = fma(-nly, ui[c], ar[s][c]);
-                ai[s][c] = fma(nlx, ui[c], ai[s][c]); ai[s][c] = fma(nly, ur[c], ai[s][c]);
-            }
-            pos[s] = mine ? T : (pos[s] == T ? P : pos[s]);    // the row that sat at the target position moves away
-            if (mine) act &= ~(1u << s);
+            for (int c = j + 1; c < 8; ++c) cfma(a[s][c], nl, u[c]);
+            if (pos[s] == T) pos[s] = P;    // the row that sat at the target position moves to where the pivot came from
         }
     }
-    // every lane has read its rows long ago (the REDUX ops above synchronise the warp): write to the new positions
+    // rows that never became a pivot: -L21, written to their (exchanged) positions
 #pragma unroll
     for (int s = 0; s < SLOTS; ++s) {
-        if ((valid >> s) & 1u) {
+        if (act[s]) {
             const int q = pos[s];
             const int sw = swz(q & 7);
             cplx* dst = M + q * LD + row0;
 #pragma unroll
-            for (int c = 0; c < 8; ++c) dst[c ^ sw] = cmake(ar[s][c], ai[s][c]);
+            for (int c = 0; c < 8; ++c) dst[c ^ sw] = a[s][c];
         }
     }
 }
 
 template <int SLOTS>
-__device__ __forceinline__ void panel_dispatch(cplx* M, int LD, int R, int row0, int lane, cplx* urow, int* piv, int* info_sh) {
+__device__ __forceinline__ void panel_dispatch(cplx* M, int LD, int R, int row0, int lane, int* pbuf, int* piv, int* info_sh) {
     const int left = R - row0;
-    if (SLOTS >= 4 && left > 96) panel_factor<(SLOTS >= 4 ? 4 : SLOTS)>(M, LD, R, row0, lane, urow, piv, info_sh);
-    else if (SLOTS >= 3 && left > 64) panel_factor<(SLOTS >= 3 ? 3 : SLOTS)>(M, LD, R, row0, lane, urow, piv, info_sh);
-    else if (SLOTS >= 2 && left > 32) panel_factor<(SLOTS >= 2 ? 2 : SLOTS)>(M, LD, R, row0, lane, urow, piv, info_sh);
-    else panel_factor<1>(M, LD, R, row0, lane, urow, piv, info_sh);
+    if (SLOTS >= 4 && left > 96) panel_factor<(SLOTS >= 4 ? 4 : SLOTS)>(M, LD, R, row0, lane, pbuf, piv, info_sh);
+    else if (SLOTS >= 3 && left > 64) panel_factor<(SLOTS >= 3 ? 3 : SLOTS)>(M, LD, R, row0, lane, pbuf, piv, info_sh);
+    else if (SLOTS >= 2 && left > 32) panel_factor<(SLOTS >= 2 ? 2 : SLOTS)>(M, LD, R, row0, lane, pbuf, piv, info_sh);
+    else panel_factor<1>(M, LD, R, row0, lane, pbuf, piv, info_sh);
+}
+
+// ---- B. row exchanges + U12 = L11^-1 A12 for one trailing column c (L11 is stored negated) -----------------------
+__device__ __forceinline__ void stepb_column(cplx* M, const int LD, const int row0, const int c, const int* pv) {
+    const int cbase = c & ~7, cin = c & 7, c_lo = row0 + 8;
+    cplx* colp = M + row0 * LD + cbase;
+    cplx u[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) u[j] = colp[j * LD + (cin ^ swz(j))];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int P = pv[j];
+        if (P >= c_lo) {
+            cplx* q = M + P * LD + cbase + (cin ^ swz(P & 7));
+            const cplx tmp = *q; *q = u[j]; u[j] = tmp;
+        } else {
+#pragma unroll
+            for (int q = j + 1; q < 8; ++q) if (P == row0 + q) { const cplx tmp = u[q]; u[q] = u[j]; u[j] = tmp; }
+        }
+    }
+#pragma unroll
+    for (int j = 1; j < 8; ++j) {
+        const cplx* lrow = M + (row0 + j) * LD + row0;
+        const int sw = swz(j);
+#pragma unroll
+        for (int i = 0; i < j; ++i) cfma(u[j], lrow[i ^ sw], u[i]);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) colp[j * LD + (cin ^ swz(j))] = u[j];
+}
+
+// per-lane fragment offsets inside 8 x 8 blocks of the swizzled matrix
+struct FragOff { int a0, a1, c0, c1, b0, b1, g; };
+
+// ---- C. tiles [t_lo, t_hi) of the trailing update of panel k over row blocks rb0.. (nrb of them) and column blocks
+//         cb0.., column-block-major so that the B fragments are reloaded only when the column block changes -------
+__device__ __forceinline__ void update_tiles(cplx* M, const int LD, const int row0, const int rb0, const int nrb, const int cb0,
+                                             const int t_lo, const int t_hi, const FragOff& fo) {
+    if (t_hi <= t_lo) return;
+    int cbk = t_lo / nrb, rbk = t_lo - cbk * nrb;
+    const cplx* Ub = M + row0 * LD + 8 * cb0;
+    cplx b0 = Ub[8 * cbk + fo.b0], b1 = Ub[8 * cbk + fo.b1];
+    for (int ti = t_lo; ti < t_hi; ++ti) {
+        cplx* rowp = M + (8 * (rb0 + rbk) + fo.g) * LD;
+        const cplx a0 = rowp[row0 + fo.a0], a1 = rowp[row0 + fo.a1];
+        cplx* pc0 = rowp + 8 * (cb0 + cbk) + fo.c0;
+        cplx* pc1 = rowp + 8 * (cb0 + cbk) + fo.c1;
+        const cplx v0 = *pc0, v1 = *pc1;
+        double cre0 = v0.x, cre1 = v1.x, cim0 = v0.y, cim1 = v1.y;
+        dmma884(cre0, cre1, a0.x, b0.x); dmma884(cim0, cim1, a0.x, b0.y);
+        dmma884(cre0, cre1, -a0.y, b0.y); dmma884(cim0, cim1, a0.y, b0.x);
+        dmma884(cre0, cre1, a1.x, b1.x); dmma884(cim0, cim1, a1.x, b1.y);
+        dmma884(cre0, cre1, -a1.y, b1.y); dmma884(cim0, cim1, a1.y, b1.x);
+        *pc0 = cmake(cre0, cim0); *pc1 = cmake(cre1, cim1);
+        if (++rbk == nrb) {
+            rbk = 0; ++cbk;
+            if (ti + 1 < t_hi) { b0 = Ub[8 * cbk + fo.b0]; b1 = Ub[8 * cbk + fo.b1]; }
+        }
+    }
 }
 
 // ---- the kernel ----------------------------------------------------------------------------------------------
 template <int SLOTS, int NW, int MINB>
 __global__ void __launch_bounds__(NW * 32, MINB) sweep_blocked_kernel(SweepParams p, int R, int NCB) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    constexpr int NT = NW * 32;
+    constexpr int NT = NW * 32, NWK = NT - 32;                   // NWK worker threads (warps 1 .. NW-1)
     const int r = p.r, m = p.m, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int LD = NCB * 8, NRB = R >> 3;
-    const int g = lane >> 2, t = lane & 3, sg = swz(g);
 
     cplx* M = reinterpret_cast<cplx*>(smem_raw);                 // R x LD, swizzled
-    cplx* urow = M + (size_t)R * LD;                             // 2 x 8 pivot-row staging
-    int* piv = reinterpret_cast<int*>(urow + 16);                // 8
-    int* info_sh = piv + 8;                                      // 1
+    int* pbuf = reinterpret_cast<int*>(M + (size_t)R * LD);      // 2 ints: pivot position staging (+ 2 pad)
+    int* piv = pbuf + 4;                                         // 2 x 8, double buffered over the panel index
+    int* info_sh = piv + 16;                                     // 1
+    // the warp that runs the critical path rotates with the CTA index so that the (up to three) resident CTAs of
+    // an SM do not all put it on the same scheduler
+    const int pw = (int)(blockIdx.x % NW);
+    const int wk = warp - (warp > pw ? 1 : 0);                   // worker index 0 .. NW-2 of the other warps
 
-    // per-lane fragment offsets inside an 8 x 8 block (row term added per tile)
-    const int offA0 = t ^ sg, offA1 = (4 + t) ^ sg;              // A-fragment: row g, k = t / 4 + t
-    const int offC0 = (2 * t) ^ sg, offC1 = (2 * t + 1) ^ sg;    // C-fragment: row g, cols 2t, 2t+1
-    const int offB0 = t * LD + (g ^ swz(t)), offB1 = (4 + t) * LD + (g ^ swz(4 + t));   // B-fragment: row k, col g
+    FragOff fo;
+    {
+        const int g = lane >> 2, t = lane & 3, sg = swz(g);
+        fo.g = g;
+        fo.a0 = t ^ sg; fo.a1 = (4 + t) ^ sg;                    // A-fragment: row g, k = t / 4 + t
+        fo.c0 = (2 * t) ^ sg; fo.c1 = (2 * t + 1) ^ sg;          // C-fragment: row g, cols 2t, 2t+1
+        fo.b0 = t * LD + (g ^ swz(t)); fo.b1 = (4 + t) * LD + (g ^ swz(4 + t));   // B-fragment: row k, col g
+    }
     const bool hasA0 = p.A0 != nullptr, hasA1 = p.A1 != nullptr, hasA2 = p.A2 != nullptr;
 
     for (long long pt = blockIdx.x; pt < p.F; pt += gridDim.x) {
         const double c0 = p.c0[pt], c1 = p.c1[pt], c2 = p.c2[pt], cb = p.cb[pt];
         // ---- assemble [A(t) | cb Br], identity on the padded diagonal ----
-#pragma unroll 2
+#pragma unroll 4
         for (int i = warp; i < r; i += NW) {
             const int sw = swz(i & 7);
             cplx* Mrow = M + i * LD;
@@ -203,78 +268,33 @@ __global__ void __launch_bounds__(NW * 32, MINB) sweep_blocked_kernel(SweepParam
         if (tid == 0) *info_sh = 0;
         __syncthreads();
 
-        // ---- blocked LU, right-hand sides eliminated alongside ----
+        // ---- blocked LU with look-ahead, right-hand sides eliminated alongside ----
+        if (warp == pw) panel_dispatch<SLOTS>(M, LD, R, 0, lane, pbuf, piv, info_sh);
         for (int k = 0; k < NRB; ++k) {
+            __syncthreads();                   // panel k is published; every warp has finished step k-1
             const int row0 = 8 * k;
-            if (warp == 0) panel_dispatch<SLOTS>(M, LD, R, row0, lane, urow, piv, info_sh);
-            __syncthreads();
-            // B. row exchanges + U12 = L11^-1 A12, one thread per trailing column (L11 is stored negated)
-            const int c_lo = row0 + 8;
-            for (int c = c_lo + tid; c < LD; c += NT) {
-                const int cbase = c & ~7, cin = c & 7;
-                cplx* colp = M + row0 * LD + cbase;
-                cplx u[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) u[j] = colp[j * LD + (cin ^ swz(j))];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int P = piv[j];
-                    if (P >= c_lo) {
-                        cplx* q = M + P * LD + cbase + (cin ^ swz(P & 7));
-                        const cplx tmp = *q; *q = u[j]; u[j] = tmp;
-                    } else {
-#pragma unroll
-                        for (int q = j + 1; q < 8; ++q) if (P == row0 + q) { const cplx tmp = u[q]; u[q] = u[j]; u[j] = tmp; }
-                    }
+            const int* pv = piv + 8 * (k & 1);
+            const int nrb = NRB - (k + 1);
+            if (warp == pw) {
+                if (nrb > 0) {                 // critical path: column block k+1, then the next panel
+                    if (lane < 8) stepb_column(M, LD, row0, row0 + 8 + lane, pv);
+                    __syncwarp();
+                    update_tiles(M, LD, row0, k + 1, nrb, k + 1, 0, nrb, fo);
+                    __syncwarp();
+                    panel_dispatch<SLOTS>(M, LD, R, row0 + 8, lane, pbuf, piv + 8 * ((k + 1) & 1), info_sh);
                 }
-#pragma unroll
-                for (int j = 1; j < 8; ++j) {
-                    const cplx* lrow = M + (row0 + j) * LD + row0;
-                    const int sw = swz(j);
-#pragma unroll
-                    for (int i = 0; i < j; ++i) cfma(u[j], lrow[i ^ sw], u[i]);
-                }
-#pragma unroll
-                for (int j = 1; j < 8; ++j) colp[j * LD + (cin ^ swz(j))] = u[j];
-                if (piv[0] != row0) colp[cin ^ swz(0)] = u[0];
-            }
-            __syncthreads();
-            // C. trailing update A22 += (-L21) U12 (complex DMMA); each warp takes a contiguous run of tiles in
-            //    column-block-major order so that the B fragments are reloaded only when the column block changes
-            const int nrb = NRB - (k + 1), ncb = NCB - (k + 1);
-            const int ntiles = nrb * ncb;
-            const int t_lo = (ntiles * warp) / NW, t_hi = (ntiles * (warp + 1)) / NW;
-            if (t_hi > t_lo) {
-                int cbk = t_lo / nrb, rbk = t_lo - cbk * nrb;
-                const cplx* Ub = M + row0 * LD + 8 * (k + 1);
-                cplx b0 = Ub[8 * cbk + offB0], b1 = Ub[8 * cbk + offB1];
-                for (int ti = t_lo; ti < t_hi; ++ti) {
-                    cplx* rowp = M + (8 * (k + 1 + rbk) + g) * LD;
-                    const cplx a0 = rowp[row0 + offA0], a1 = rowp[row0 + offA1];
-                    cplx* pc0 = rowp + 8 * (k + 1 + cbk) + offC0;
-                    cplx* pc1 = rowp + 8 * (k + 1 + cbk) + offC1;
-                    const cplx v0 = *pc0, v1 = *pc1;
-                    double cre0 = v0.x, cre1 = v1.x, cim0 = v0.y, cim1 = v1.y;
-                    dmma884(cre0, cre1, a0.x, b0.x); dmma884(cim0, cim1, a0.x, b0.y);
-                    dmma884(cre0, cre1, -a0.y, b0.y); dmma884(cim0, cim1, a0.y, b0.x);
-                    dmma884(cre0, cre1, a1.x, b1.x); dmma884(cim0, cim1, a1.x, b1.y);
-                    dmma884(cre0, cre1, -a1.y, b1.y); dmma884(cim0, cim1, a1.y, b1.x);
-                    *pc0 = cmake(cre0, cim0); *pc1 = cmake(cre1, cim1);
-                    if (++rbk == nrb) {
-                        rbk = 0; ++cbk;
-                        if (ti + 1 < t_hi) { b0 = Ub[8 * cbk + offB0]; b1 = Ub[8 * cbk + offB1]; }
-                    }
+            } else if (NW > 1) {               // everything to the right of column block k+1 (all of it after the last panel)
+                const int cb0 = nrb > 0 ? k + 2 : k + 1;
+                for (int c = 8 * cb0 + wk * 32 + lane; c < LD; c += NWK) stepb_column(M, LD, row0, c, pv);
+                if (nrb > 0) {
+                    asm volatile("bar.sync 1, %0;" :: "n"(NWK > 0 ? NWK : 32) : "memory");
+                    const int ntiles = nrb * (NCB - cb0);
+                    update_tiles(M, LD, row0, k + 1, nrb, cb0, (ntiles * wk) / (NW - 1), (ntiles * (wk + 1)) / (NW - 1), fo);
                 }
             }
-            __syncthreads();
         }
+        __syncthreads();
 
-#ifdef MF_BLOCKED_DEBUG
-        if (p.ws_stride == -12345 && pt == 0) {          // debug: dump the factored matrix (logical layout) and pivots
-            for (int idx = tid; idx < R * LD; idx += NT) p.ws[idx] = M[mphys(idx / LD, idx % LD, LD)];
-            __syncthreads();
-        }
-#endif
         // ---- back substitution U x = y, one warp per right-hand side, solution kept in registers ----
         for (int c = warp; c < m; c += NW) {
             double yr[SLOTS], yi[SLOTS];
@@ -354,7 +374,7 @@ BlockedGeom blocked_geom(int r, int m) {
     BlockedGeom gm;
     gm.R = (r + 7) / 8 * 8;
     gm.NCB = gm.R / 8 + (m + 7) / 8;
-    gm.smem = sizeof(cplx) * ((size_t)gm.R * gm.NCB * 8 + 16) + 64;
+    gm.smem = sizeof(cplx) * ((size_t)gm.R * gm.NCB * 8) + 128;
     return gm;
 }
 
