@@ -107,14 +107,34 @@ gemm_tn_kernel(const cplx* __restrict__ A, long long lda, int ra, const cplx* __
         }
 }
 
-__global__ void reduce_partials_kernel(const cplx* __restrict__ part, int nsplit, int ra, int rb, cplx* __restrict__ C, long long ldc) {
-    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    long long total = (long long)ra * rb;
-    if (idx >= total) return;
-    cplx acc = cmake(0.0, 0.0);
-    for (int s = 0; s < nsplit; ++s) acc = cadd(acc, part[(long long)s * total + idx]);   // fixed order: deterministic
-    int i = (int)(idx / rb), j = (int)(idx - (long long)i * rb);
-    C[i * ldc + j] = acc;
+// C = sum over splits of part[s] in a FIXED order (deterministic: replicated r x r factorisations on several ranks see
+// bit-identical input).  One CTA per 32 consecutive elements: lane -> element (coalesced 512-byte rows), warp w sums
+// splits w, w+8, ... with independent loads in flight; the eight warp partials are combined in warp order.
+constexpr int RED_WARPS = 8;
+__global__ void __launch_bounds__(RED_WARPS * 32)
+reduce_partials_kernel(const cplx* __restrict__ part, int nsplit, int ra, int rb, cplx* __restrict__ C, long long ldc) {
+    __shared__ cplx red[RED_WARPS][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long total = (long long)ra * rb;
+    const long long idx = (long long)blockIdx.x * 32 + lane;
+    cplx acc0 = cmake(0.0, 0.0), acc1 = cmake(0.0, 0.0);
+    if (idx < total) {
+        int s = warp;
+        for (; s + RED_WARPS < nsplit; s += 2 * RED_WARPS) {
+            const cplx v0 = part[(long long)s * total + idx], v1 = part[(long long)(s + RED_WARPS) * total + idx];
+            acc0 = cadd(acc0, v0); acc1 = cadd(acc1, v1);
+        }
+        if (s < nsplit) acc0 = cadd(acc0, part[(long long)s * total + idx]);
+    }
+    red[warp][lane] = cadd(acc0, acc1);
+    __syncthreads();
+    if (warp == 0 && idx < total) {
+        cplx acc = red[0][lane];
+#pragma unroll
+        for (int w = 1; w < RED_WARPS; ++w) acc = cadd(acc, red[w][lane]);
+        const int i = (int)(idx / rb), j = (int)(idx - (long long)i * rb);
+        C[i * ldc + j] = acc;
+    }
 }
 
 void tn_plan(int ra, int rb, long long n, int& tiles, int& nsplit, long long& rows_per_split) {
@@ -248,7 +268,7 @@ extern "C" int mf_gemm_tn_c128(const mf_c128* A, int64_t lda, int ra, const mf_c
     gemm_tn_kernel<<<grid, TN_THREADS, smem, st>>>((const cplx*)A, lda, ra, (const cplx*)B, ldb, rb, n, rps, conj_a, (cplx*)ws);
     MF_CHECK_LAUNCH();
     long long total = (long long)ra * rb;
-    reduce_partials_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>((const cplx*)ws, nsplit, ra, rb, (cplx*)C, ldc);
+    reduce_partials_kernel<<<(unsigned)((total + 31) / 32), RED_WARPS * 32, 0, st>>>((const cplx*)ws, nsplit, ra, rb, (cplx*)C, ldc);
     MF_CHECK_LAUNCH();
     return 0;
 }

@@ -322,8 +322,10 @@ def orthonormalize(s: torch.Tensor, truncation_tol: float = 0.0, group=None, n_g
     n_loc, r = s.shape
     eps = np.finfo(np.float64).eps
     d = torch.empty(r, dtype=torch.float64, device=dev)
-    stats = torch.zeros(2, dtype=torch.float64, device=dev)
-    info = torch.zeros(1, dtype=torch.int32, device=dev)
+    # one 32-byte flag block so that a pass costs ONE device->host read: [0:16) stats (2 doubles), [16:20) potrf info
+    flags = torch.zeros(32, dtype=torch.uint8, device=dev)
+    stats = flags[:16].view(torch.float64)
+    info = flags[16:20].view(torch.int32)
     x = s
     r_tot = None
     shifts = []
@@ -336,14 +338,15 @@ def orthonormalize(s: torch.Tensor, truncation_tol: float = 0.0, group=None, n_g
             gw = g.clone()
             _ffi.check(lib.mf_equilibrate_c128(_ptr(gw), gw.stride(0), r, shift, _ptr(d), _ptr(stats), _stream()), "mf_equilibrate_c128")
             _ffi.check(lib.mf_potrf_upper_c128(_ptr(gw), gw.stride(0), r, _ptr(info), _stream()), "mf_potrf_upper_c128")
-            if int(info.item()) == 0:
+            host_flags = flags.cpu()
+            if int(host_flags[16:20].view(torch.int32)[0]) == 0:
                 break
             shift = 64.0 * eps * r if shift == 0.0 else shift * 100.0
             if shift > 1e-2:
                 raise _ffi.MorfemB200Error("orthonormalize: Cholesky breakdown persists (snapshot block numerically rank deficient "
                                            "beyond what shifted CholeskyQR can repair)")
         shifts.append(shift)
-        departure = float(stats[0].item())
+        departure = float(host_flags[:8].view(torch.float64)[0])
         # R = Rtilde D^-1 (undo the equilibration), Rinv = R^-1
         _ffi.check(lib.mf_scale_cols_c128(_ptr(gw), gw.stride(0), r, r, _ptr(d), -1, _stream()), "mf_scale_cols_c128")
         rinv = torch.empty((r, r), dtype=C128, device=dev)
