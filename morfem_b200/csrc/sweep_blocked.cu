@@ -21,26 +21,10 @@
 // The right-hand sides ride along as extra column blocks, so L is never needed again; back substitution
 // (`lu_solve`, implementation.py:478) and the S-parameter algebra (test_helpers.py:9-14) form the epilogue.
 // Roofline: FP64 pipe.  Operators are L2 resident; per point the kernel writes 16 m^2 bytes (+ 16 r m with X).
-#include "sweep_common.cuh"
+#include "sweep_blocked.cuh"
 #include <stdlib.h>
 
 namespace {
-
-constexpr unsigned FULL = 0xffffffffu;
-
-__device__ __forceinline__ int swz(int g) { return (((g ^ (g >> 2)) & 1) << 2) | (g & 3); }
-__device__ __forceinline__ int mphys(int row, int col, int LD) { return row * LD + (col & ~7) + ((col & 7) ^ swz(row & 7)); }
-
-// 1/a by Smith's formula with reciprocals (two correctly rounded reciprocals instead of three divisions)
-__device__ __noinline__ cplx crecip2(cplx a) {
-    if (fabs(a.x) >= fabs(a.y)) {
-        const double ia = 1.0 / a.x, t = a.y * ia, d = fma(a.y, t, a.x), id = 1.0 / d;
-        return cmake(id, -t * id);
-    } else {
-        const double ib = 1.0 / a.y, t = a.x * ib, d = fma(a.x, t, a.y), id = 1.0 / d;
-        return cmake(t * id, -id);
-    }
-}
 
 // ---- A. panel factorisation by one warp -------------------------------------------------------------------
 // Rows row0 .. R-1, columns row0 .. row0+7, one (or a few) rows per lane, held in registers.  On exit the panel holds
@@ -146,65 +130,6 @@ __device__ __forceinline__ void panel_dispatch(cplx* M, int LD, int R, int row0,
     else if (SLOTS >= 3 && left > 64) panel_factor<(SLOTS >= 3 ? 3 : SLOTS)>(M, LD, R, row0, lane, pbuf, piv, info_sh);
     else if (SLOTS >= 2 && left > 32) panel_factor<(SLOTS >= 2 ? 2 : SLOTS)>(M, LD, R, row0, lane, pbuf, piv, info_sh);
     else panel_factor<1>(M, LD, R, row0, lane, pbuf, piv, info_sh);
-}
-
-// ---- B. row exchanges + U12 = L11^-1 A12 for one trailing column c (L11 is stored negated) -----------------------
-__device__ __forceinline__ void stepb_column(cplx* M, const int LD, const int row0, const int c, const int* pv) {
-    const int cbase = c & ~7, cin = c & 7, c_lo = row0 + 8;
-    cplx* colp = M + row0 * LD + cbase;
-    cplx u[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) u[j] = colp[j * LD + (cin ^ swz(j))];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const int P = pv[j];
-        if (P >= c_lo) {
-            cplx* q = M + P * LD + cbase + (cin ^ swz(P & 7));
-            const cplx tmp = *q; *q = u[j]; u[j] = tmp;
-        } else {
-#pragma unroll
-            for (int q = j + 1; q < 8; ++q) if (P == row0 + q) { const cplx tmp = u[q]; u[q] = u[j]; u[j] = tmp; }
-        }
-    }
-#pragma unroll
-    for (int j = 1; j < 8; ++j) {
-        const cplx* lrow = M + (row0 + j) * LD + row0;
-        const int sw = swz(j);
-#pragma unroll
-        for (int i = 0; i < j; ++i) cfma(u[j], lrow[i ^ sw], u[i]);
-    }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) colp[j * LD + (cin ^ swz(j))] = u[j];
-}
-
-// per-lane fragment offsets inside 8 x 8 blocks of the swizzled matrix
-struct FragOff { int a0, a1, c0, c1, b0, b1, g; };
-
-// ---- C. tiles [t_lo, t_hi) of the trailing update of panel k over row blocks rb0.. (nrb of them) and column blocks
-//         cb0.., column-block-major so that the B fragments are reloaded only when the column block changes -------
-__device__ __forceinline__ void update_tiles(cplx* M, const int LD, const int row0, const int rb0, const int nrb, const int cb0,
-                                             const int t_lo, const int t_hi, const FragOff& fo) {
-    if (t_hi <= t_lo) return;
-    int cbk = t_lo / nrb, rbk = t_lo - cbk * nrb;
-    const cplx* Ub = M + row0 * LD + 8 * cb0;
-    cplx b0 = Ub[8 * cbk + fo.b0], b1 = Ub[8 * cbk + fo.b1];
-    for (int ti = t_lo; ti < t_hi; ++ti) {
-        cplx* rowp = M + (8 * (rb0 + rbk) + fo.g) * LD;
-        const cplx a0 = rowp[row0 + fo.a0], a1 = rowp[row0 + fo.a1];
-        cplx* pc0 = rowp + 8 * (cb0 + cbk) + fo.c0;
-        cplx* pc1 = rowp + 8 * (cb0 + cbk) + fo.c1;
-        const cplx v0 = *pc0, v1 = *pc1;
-        double cre0 = v0.x, cre1 = v1.x, cim0 = v0.y, cim1 = v1.y;
-        dmma884(cre0, cre1, a0.x, b0.x); dmma884(cim0, cim1, a0.x, b0.y);
-        dmma884(cre0, cre1, -a0.y, b0.y); dmma884(cim0, cim1, a0.y, b0.x);
-        dmma884(cre0, cre1, a1.x, b1.x); dmma884(cim0, cim1, a1.x, b1.y);
-        dmma884(cre0, cre1, -a1.y, b1.y); dmma884(cim0, cim1, a1.y, b1.x);
-        *pc0 = cmake(cre0, cim0); *pc1 = cmake(cre1, cim1);
-        if (++rbk == nrb) {
-            rbk = 0; ++cbk;
-            if (ti + 1 < t_hi) { b0 = Ub[8 * cbk + fo.b0]; b1 = Ub[8 * cbk + fo.b1]; }
-        }
-    }
 }
 
 // ---- the kernel ----------------------------------------------------------------------------------------------
@@ -357,17 +282,6 @@ __global__ void __launch_bounds__(NW * 32, MINB) sweep_blocked_kernel(SweepParam
     }
 }
 
-// One thread per point: S <- 2 (I + Z^-1)^-1 - I in place (Z left in S by the sweep kernel).
-template <int MMAX>
-__global__ void __launch_bounds__(128) gsm_finish_kernel(cplx* __restrict__ S, int m, long long F) {
-    const long long pt = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (pt >= F) return;
-    cplx z[MMAX * MMAX], scratch[2 * MMAX * MMAX];
-    cplx* sp = S + pt * (long long)m * m;
-    for (int e = 0; e < m * m; ++e) z[e] = sp[e];
-    gsm_from_impedance(z, scratch, m, sp);
-}
-
 struct BlockedGeom { int R, NCB; size_t smem; };
 
 BlockedGeom blocked_geom(int r, int m) {
@@ -389,29 +303,30 @@ int launch_blocked(const SweepParams& p, const BlockedGeom& gm, cudaStream_t str
     if (grid > p.F) grid = p.F;
     kern<<<(unsigned)grid, NW * 32, gm.smem, stream>>>(p, gm.R, gm.NCB);
     MF_CHECK_LAUNCH();
-    if (p.S) {
-        const unsigned blocks = (unsigned)((p.F + 127) / 128);
-        if (p.m <= 2) gsm_finish_kernel<2><<<blocks, 128, 0, stream>>>(p.S, p.m, p.F);
-        else if (p.m <= 4) gsm_finish_kernel<4><<<blocks, 128, 0, stream>>>(p.S, p.m, p.F);
-        else if (p.m <= 8) gsm_finish_kernel<8><<<blocks, 128, 0, stream>>>(p.S, p.m, p.F);
-        else gsm_finish_kernel<MF_MAX_PORTS><<<blocks, 128, 0, stream>>>(p.S, p.m, p.F);
-        MF_CHECK_LAUNCH();
-    }
+    if (p.S) return gsm_finish_launch(p.S, p.m, p.F, stream);
     return 0;
 }
 
 }  // namespace
 
-bool sweep_blocked_supports(int r, int m) {
+// sweep_stream.cu: the same algorithm with the matrix streamed from an L2-resident workspace (r up to 512)
+bool sweep_stream_supports(int r, int m);
+size_t sweep_stream_ws_bytes(int r, int m, long long F);
+int sweep_stream_launch(const SweepParams& p, size_t ws_bytes, cudaStream_t stream);
+
+static bool blocked_fits_smem(int r, int m) {
     if (r < 1 || m < 1 || m > MF_MAX_PORTS) return false;
     const BlockedGeom gm = blocked_geom(r, m);
     return gm.R <= 128 && gm.smem <= 226 * 1024;
 }
 
-size_t sweep_blocked_ws_bytes(int, int, long long) { return 0; }
+bool sweep_blocked_supports(int r, int m) { return blocked_fits_smem(r, m) || sweep_stream_supports(r, m); }
+
+size_t sweep_blocked_ws_bytes(int r, int m, long long F) { return blocked_fits_smem(r, m) ? 0 : sweep_stream_ws_bytes(r, m, F); }
 
 int sweep_blocked_launch(const SweepParams& p_in, size_t ws_bytes, cudaStream_t stream) {
     SweepParams p = p_in;
+    if (!blocked_fits_smem(p.r, p.m) || getenv("MF_SWEEP_FORCE_STREAM")) return sweep_stream_launch(p, ws_bytes, stream);
     const BlockedGeom gm = blocked_geom(p.r, p.m);
 #ifdef MF_BLOCKED_DEBUG
     if (getenv("MF_BLOCKED_DUMP") && p.ws && ws_bytes >= sizeof(cplx) * gm.R * gm.NCB * 8) p.ws_stride = -12345;
