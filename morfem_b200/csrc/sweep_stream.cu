@@ -35,7 +35,7 @@ struct CandKey { double v; int pos; int pad; };
 template <int SL>
 __device__ __forceinline__ void panel_factor_mw(cplx* PB, const int LDp, const int rows, const int row0, const int tid,
                                                 CandKey* candk, cplx* candrow, int* pvl, int* info_sh, const int info_base) {
-    const int warp = tid >> 5;
+    const int lane = tid & 31, warp = tid >> 5;
     cplx a[SL][8];
     int pos[SL];
     bool act[SL];
@@ -86,13 +86,29 @@ __device__ __forceinline__ void panel_factor_mw(cplx* PB, const int LDp, const i
                 }
         }
         __syncthreads();
-        double gv = -2.0; int P = 0x7fffffff, gw = 0;
-#pragma unroll
-        for (int w = 0; w < ST_NW; ++w) {
-            const double v = *reinterpret_cast<volatile double*>(&ck[w].v);
-            const int pp = *reinterpret_cast<volatile int*>(&ck[w].pos);
-            if (v > gv || (v == gv && pp < P)) { gv = v; P = pp; gw = w; }
+        // global winner among the NW warp candidates: lane w looks at candidate w, then the same warp arg-max
+        double cv = -2.0; int cp = 0x7fffffff;
+        if (lane < ST_NW) {
+            const unsigned cks = (unsigned)__cvta_generic_to_shared(ck + lane);
+            long long pbits;
+            asm volatile("ld.volatile.shared.v2.b64 {%0, %1}, [%2];" : "=d"(cv), "=l"(pbits) : "r"(cks));
+            cp = (int)pbits;
         }
+        const int chi = __double2hiint(cv);
+        const int chmax = __reduce_max_sync(FULL, chi);
+        bool cown = (chi == chmax);
+        if (__popc(__ballot_sync(FULL, cown)) != 1) {
+            const unsigned clo = (unsigned)__double2loint(cv);
+            const unsigned clmax = __reduce_max_sync(FULL, cown ? clo : 0u);
+            cown = cown && (clo == clmax);
+            if (__popc(__ballot_sync(FULL, cown)) != 1) {
+                const int cpmin = __reduce_min_sync(FULL, cown ? cp : 0x7fffffff);
+                cown = cown && (cp == cpmin);
+            }
+        }
+        const int gw = __ffs(__ballot_sync(FULL, cown)) - 1;
+        const int P = __shfl_sync(FULL, cp, gw);
+        const double gv = __shfl_sync(FULL, cv, gw);
         if (own && warp == gw) {                     // this lane held the pivot row: retire the slot
 #pragma unroll
             for (int s = 0; s < SL; ++s) if (s == bs) act[s] = false;
@@ -167,22 +183,31 @@ __global__ void __launch_bounds__(ST_NT, 1) sweep_stream_kernel(SweepParams p, i
     for (long long pt = blockIdx.x; pt < p.F; pt += gridDim.x) {
         const double c0 = p.c0[pt], c1 = p.c1[pt], c2 = p.c2[pt], cb = p.cb[pt];
         // ---- assemble [A(t) | cb Br] into the slot, identity on the padded diagonal ----
+        constexpr int RPLA = (NBO == 32) ? 8 : 16;                // row elements per lane (R <= 32 RPLA)
         for (int i = warp; i < R; i += ST_NW) {
             cplx* Arow = A + (long long)i * LD;
             const long long rowoff = (long long)i * p.lda;
-            for (int j = lane; j < LD; j += 32) {
-                cplx v = cmake(0.0, 0.0);
-                if (j < R) {
-                    if (i < r && j < r) {
-                        if (hasA0) { const cplx x = __ldg(p.A0 + rowoff + j); v.x = c0 * x.x; v.y = c0 * x.y; }
-                        if (hasA1) { const cplx x = __ldg(p.A1 + rowoff + j); v.x = fma(c1, x.x, v.x); v.y = fma(c1, x.y, v.y); }
-                        if (hasA2) { const cplx x = __ldg(p.A2 + rowoff + j); v.x = fma(c2, x.x, v.x); v.y = fma(c2, x.y, v.y); }
-                    } else if (i == j) v.x = 1.0;
-                } else if (i < r && j - R < m) {
-                    const cplx b = __ldg(p.Br + (long long)i * p.ldb + (j - R));
-                    v.x = cb * b.x; v.y = cb * b.y;
+            if (i < r) {
+                cplx v[RPLA];
+#pragma unroll
+                for (int q = 0; q < RPLA; ++q) {
+                    const int j = lane + 32 * q;
+                    v[q] = cmake(0.0, 0.0);
+                    if (j < r) {
+                        if (hasA0) { const cplx x = __ldg(p.A0 + rowoff + j); v[q].x = c0 * x.x; v[q].y = c0 * x.y; }
+                        if (hasA1) { const cplx x = __ldg(p.A1 + rowoff + j); v[q].x = fma(c1, x.x, v[q].x); v[q].y = fma(c1, x.y, v[q].y); }
+                        if (hasA2) { const cplx x = __ldg(p.A2 + rowoff + j); v[q].x = fma(c2, x.x, v[q].x); v[q].y = fma(c2, x.y, v[q].y); }
+                    }
                 }
-                Arow[j] = v;
+#pragma unroll
+                for (int q = 0; q < RPLA; ++q) { const int j = lane + 32 * q; if (j < R) Arow[j] = v[q]; }
+                for (int j = lane; j < LD - R; j += 32) {
+                    cplx b = cmake(0.0, 0.0);
+                    if (j < m) { const cplx x = __ldg(p.Br + (long long)i * p.ldb + j); b.x = cb * x.x; b.y = cb * x.y; }
+                    Arow[R + j] = b;
+                }
+            } else {
+                for (int j = lane; j < LD; j += 32) Arow[j] = cmake(j == i ? 1.0 : 0.0, 0.0);
             }
         }
         if (tid == 0) *info_sh = 0;
@@ -323,17 +348,26 @@ __global__ void __launch_bounds__(ST_NT, 1) sweep_stream_kernel(SweepParams p, i
 #pragma unroll
                     for (int kk = 0; kk < NBO / 4; ++kk) af[kk] = arow[(4 * kk + t) ^ sg];      // (4kk + t) ^ swz(g): same 8-block
                     cplx* crow = A + (long long)(col0 + 8 * rb + g) * LD + cc0 + 2 * t;
-                    for (int ct = 0; ct < cw / 8; ++ct) {
-                        cplx* pc = crow + 8 * ct;
-                        const cplx v0 = pc[0], v1 = pc[1];
-                        double cre0 = v0.x, cre1 = v1.x, cim0 = v0.y, cim1 = v1.y;
+                    const int nct = cw / 8;
+                    for (int ct0 = 0; ct0 < nct; ct0 += 4) {
+                        cplx v[4][2];
 #pragma unroll
-                        for (int kk = 0; kk < NBO / 4; ++kk) {
-                            const cplx b = UB[(4 * kk + t) * ST_CW + 8 * ct + (g ^ swz((4 * kk + t) & 7))];
-                            dmma884(cre0, cre1, af[kk].x, b.x); dmma884(cim0, cim1, af[kk].x, b.y);
-                            dmma884(cre0, cre1, -af[kk].y, b.y); dmma884(cim0, cim1, af[kk].y, b.x);
+                        for (int q = 0; q < 4; ++q)
+                            if (ct0 + q < nct) { v[q][0] = crow[8 * (ct0 + q)]; v[q][1] = crow[8 * (ct0 + q) + 1]; }
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            if (ct0 + q < nct) {
+                                const int ct = ct0 + q;
+                                double cre0 = v[q][0].x, cre1 = v[q][1].x, cim0 = v[q][0].y, cim1 = v[q][1].y;
+#pragma unroll
+                                for (int kk = 0; kk < NBO / 4; ++kk) {
+                                    const cplx b = UB[(4 * kk + t) * ST_CW + 8 * ct + (g ^ swz((4 * kk + t) & 7))];
+                                    dmma884(cre0, cre1, af[kk].x, b.x); dmma884(cim0, cim1, af[kk].x, b.y);
+                                    dmma884(cre0, cre1, -af[kk].y, b.y); dmma884(cim0, cim1, af[kk].y, b.x);
+                                }
+                                crow[8 * ct] = cmake(cre0, cim0); crow[8 * ct + 1] = cmake(cre1, cim1);
+                            }
                         }
-                        pc[0] = cmake(cre0, cim0); pc[1] = cmake(cre1, cim1);
                     }
                 }
                 __syncthreads();
