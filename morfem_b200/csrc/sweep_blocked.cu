@@ -162,28 +162,46 @@ __global__ void __launch_bounds__(NW * 32, MINB) sweep_blocked_kernel(SweepParam
     for (long long pt = blockIdx.x; pt < p.F; pt += gridDim.x) {
         const double c0 = p.c0[pt], c1 = p.c1[pt], c2 = p.c2[pt], cb = p.cb[pt];
         // ---- assemble [A(t) | cb Br], identity on the padded diagonal ----
-#pragma unroll 4
-        for (int i = warp; i < r; i += NW) {
-            const int sw = swz(i & 7);
-            cplx* Mrow = M + i * LD;
-            const long long rowoff = (long long)i * p.lda;
+        // (all loads of four rows are issued before the first use: the operators come from L2, ~1 us away)
+        constexpr int RG = 4;
+        for (int i0 = warp; i0 < r; i0 += NW * RG) {
+            cplx x0[RG][SLOTS], x2[RG][SLOTS], xb[RG];
 #pragma unroll
-            for (int jj = 0; jj < SLOTS; ++jj) {
-                const int j = lane + 32 * jj;
-                if (j < R) {
-                    cplx v = cmake(0.0, 0.0);
-                    if (j < r) {
-                        if (hasA0) { const cplx a = __ldg(p.A0 + rowoff + j); v.x = c0 * a.x; v.y = c0 * a.y; }
-                        if (hasA1) { const cplx a = __ldg(p.A1 + rowoff + j); v.x = fma(c1, a.x, v.x); v.y = fma(c1, a.y, v.y); }
-                        if (hasA2) { const cplx a = __ldg(p.A2 + rowoff + j); v.x = fma(c2, a.x, v.x); v.y = fma(c2, a.y, v.y); }
+            for (int q = 0; q < RG; ++q) {
+                const int i = i0 + q * NW;
+                const long long rowoff = (long long)i * p.lda;
+#pragma unroll
+                for (int jj = 0; jj < SLOTS; ++jj) {
+                    const int j = lane + 32 * jj;
+                    const bool ok = i < r && j < r;
+                    x0[q][jj] = (ok && hasA0) ? __ldg(p.A0 + rowoff + j) : cmake(0.0, 0.0);
+                    x2[q][jj] = (ok && hasA2) ? __ldg(p.A2 + rowoff + j) : cmake(0.0, 0.0);
+                }
+                xb[q] = (i < r && lane < m) ? __ldg(p.Br + (long long)i * p.ldb + lane) : cmake(0.0, 0.0);
+            }
+#pragma unroll
+            for (int q = 0; q < RG; ++q) {
+                const int i = i0 + q * NW;
+                if (i < r) {
+                    const int sw = swz(i & 7);
+                    cplx* Mrow = M + i * LD;
+#pragma unroll
+                    for (int jj = 0; jj < SLOTS; ++jj) {
+                        const int j = lane + 32 * jj;
+                        if (j < R) Mrow[(j & ~7) + ((j & 7) ^ sw)] = cmake(fma(c2, x2[q][jj].x, c0 * x0[q][jj].x), fma(c2, x2[q][jj].y, c0 * x0[q][jj].y));
                     }
-                    Mrow[(j & ~7) + ((j & 7) ^ sw)] = v;
+                    if (lane < LD - R) Mrow[R + (lane & ~7) + ((lane & 7) ^ sw)] = cmake(cb * xb[q].x, cb * xb[q].y);
                 }
             }
-            for (int j = lane; j < LD - R; j += 32) {
-                cplx v = cmake(0.0, 0.0);
-                if (j < m) { const cplx b = __ldg(p.Br + (long long)i * p.ldb + j); v.x = cb * b.x; v.y = cb * b.y; }
-                Mrow[R + (j & ~7) + ((j & 7) ^ sw)] = v;
+        }
+        if (hasA1) {                        // rarely present (the reference's a1 is an empty matrix): same thread, same elements
+            for (int i = warp; i < r; i += NW) {
+                const int sw = swz(i & 7);
+                for (int j = lane; j < r; j += 32) {
+                    const cplx a = __ldg(p.A1 + (long long)i * p.lda + j);
+                    cplx* e = M + i * LD + (j & ~7) + ((j & 7) ^ sw);
+                    cplx v = *e; v.x = fma(c1, a.x, v.x); v.y = fma(c1, a.y, v.y); *e = v;
+                }
             }
         }
         for (int i = r + warp; i < R; i += NW) {
@@ -220,32 +238,47 @@ __global__ void __launch_bounds__(NW * 32, MINB) sweep_blocked_kernel(SweepParam
         }
         __syncthreads();
 
-        // ---- back substitution U x = y, one warp per right-hand side, solution kept in registers ----
+        // ---- back substitution U x = y (`lu_solve`), one warp per right-hand side, solution in registers (row i in
+        //      lane i % 32, slot i / 32), processed in blocks of 8 rows: the 8 x 8 triangular system of a block is
+        //      solved redundantly by every lane from broadcast loads, then each lane updates its own rows with the
+        //      8 new unknowns -- 8 dependent steps per block instead of 8 shuffle round trips ----
         for (int c = warp; c < m; c += NW) {
-            double yr[SLOTS], yi[SLOTS];
+            cplx y[SLOTS];
 #pragma unroll
             for (int s = 0; s < SLOTS; ++s) {
                 const int i = s * 32 + lane;
-                cplx v = cmake(0.0, 0.0);
-                if (i < R) v = M[mphys(i, R + c, LD)];
-                yr[s] = v.x; yi[s] = v.y;
+                y[s] = i < R ? M[mphys(i, R + c, LD)] : cmake(0.0, 0.0);
             }
 #pragma unroll
             for (int ks = SLOTS - 1; ks >= 0; --ks) {
-                for (int kl = 31; kl >= 0; --kl) {
-                    const int k = ks * 32 + kl;
-                    if (k >= R) continue;
-                    const cplx inv = M[mphys(k, k, LD)];
-                    const cplx xk = cmul(cmake(yr[ks], yi[ks]), inv);
-                    const double xr = __shfl_sync(FULL, xk.x, kl), xi = __shfl_sync(FULL, xk.y, kl);
-                    if (lane == kl) { yr[ks] = xr; yi[ks] = xi; }
 #pragma unroll
-                    for (int s = 0; s <= ks; ++s) {
-                        const int i = s * 32 + lane;
-                        if (i < k) {
-                            const cplx u = M[mphys(i, k, LD)];
-                            yr[s] = fma(-u.x, xr, yr[s]); yr[s] = fma(u.y, xi, yr[s]);
-                            yi[s] = fma(-u.x, xi, yi[s]); yi[s] = fma(-u.y, xr, yi[s]);
+                for (int kq = 3; kq >= 0; --kq) {
+                    const int kb8 = ks * 32 + kq * 8;                    // first row of the block
+                    if (kb8 < R) {
+                        cplx x[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) { x[j].x = __shfl_sync(FULL, y[ks].x, kq * 8 + j); x[j].y = __shfl_sync(FULL, y[ks].y, kq * 8 + j); }
+#pragma unroll
+                        for (int j = 7; j >= 0; --j) {
+                            const cplx* urow = M + (kb8 + j) * LD + kb8;
+                            const int sw = swz(j);
+#pragma unroll
+                            for (int jj = j + 1; jj < 8; ++jj) cfms(x[j], urow[jj ^ sw], x[jj]);
+                            x[j] = cmul(x[j], urow[j ^ sw]);             // reciprocal pivot on the diagonal
+                        }
+#pragma unroll
+                        for (int s = 0; s <= ks; ++s) {
+                            const int i = s * 32 + lane;
+                            if (i < kb8) {
+                                const cplx* urow = M + i * LD + kb8;
+                                const int sw = swz(i & 7);
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) cfms(y[s], urow[j ^ sw], x[j]);
+                            }
+                        }
+                        if ((lane >> 3) == kq) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) if ((lane & 7) == j) y[ks] = x[j];
                         }
                     }
                 }
@@ -254,9 +287,8 @@ __global__ void __launch_bounds__(NW * 32, MINB) sweep_blocked_kernel(SweepParam
             for (int s = 0; s < SLOTS; ++s) {
                 const int i = s * 32 + lane;
                 if (i < r) {
-                    const cplx x = cmake(yr[s], yi[s]);
-                    M[mphys(i, R + c, LD)] = x;
-                    if (p.X) p.X[(pt * r + i) * m + c] = x;
+                    M[mphys(i, R + c, LD)] = y[s];
+                    if (p.X) p.X[(pt * r + i) * m + c] = y[s];
                 }
             }
         }
