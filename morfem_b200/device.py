@@ -295,27 +295,46 @@ def _allreduce(t: torch.Tensor, group) -> None:
     dist.all_reduce(torch.view_as_real(t), op=dist.ReduceOp.SUM, group=group)
 
 
-@dataclass
 class BasisInfo:
-    sigma: np.ndarray          # singular values of the snapshot block (descending)
-    passes: int                # Cholesky-QR passes used
-    shifts: list               # diagonal shift used in each pass (0 = plain Cholesky)
-    jacobi_sweeps: int
-    kept: int                  # columns kept after truncation
+    """Diagnostics of the basis stage.  ``sigma`` (singular values of the snapshot block, descending) and
+    ``jacobi_sweeps`` are produced on the device and fetched lazily, so that building the basis does not force a
+    device->host synchronisation."""
+
+    def __init__(self, sigma, passes, shifts, jacobi_sweeps, kept):
+        self._sigma = sigma            # device tensor or ndarray
+        self.passes = passes           # Cholesky-QR passes used
+        self.shifts = shifts           # diagonal shift used in each pass (0 = plain Cholesky)
+        self._sweeps = jacobi_sweeps   # device tensor or int
+        self.kept = kept               # columns kept after truncation
+
+    @property
+    def sigma(self) -> np.ndarray:
+        if isinstance(self._sigma, torch.Tensor):
+            self._sigma = self._sigma.cpu().numpy()
+        return self._sigma
+
+    @property
+    def jacobi_sweeps(self) -> int:
+        if isinstance(self._sweeps, torch.Tensor):
+            self._sweeps = int(self._sweeps.item())
+        return self._sweeps
 
 
-def orthonormalize(s: torch.Tensor, truncation_tol: float = 0.0, group=None, n_global: Optional[int] = None,
-                   max_passes: int = 6) -> tuple[torch.Tensor, BasisInfo]:
-    """Orthonormal basis of span(S) with columns ordered like the left singular vectors of S.
+@dataclass
+class CholQR:
+    """Result of the Cholesky-QR passes: ``S = x @ r_tot`` with ``x @ rinv`` orthonormal to rounding
+    (``rinv`` inverts the triangular factor of the LAST pass, whose input was ``x``)."""
+    x: torch.Tensor
+    r_tot: torch.Tensor
+    rinv: torch.Tensor
+    passes: int
+    shifts: list
 
-    B200 replacement of ``np.linalg.svd(S, full_matrices=False)[0]`` (implementation.py:226/298/210):
-    Cholesky-QR passes ``G = X^H X`` (DMMA, all-reduced over row shards) -> equilibrated (shifted if needed)
+
+def cholesky_qr(s: torch.Tensor, group=None, max_passes: int = 6) -> CholQR:
+    """Cholesky-QR passes ``G = X^H X`` (DMMA, all-reduced over row shards) -> equilibrated (shifted if needed)
     Cholesky -> ``X <- X R^-1`` until the input of a pass is already near-orthonormal (CholeskyQR2, or shifted
-    CholeskyQR3 for cond(S) >~ 1e8); then a one-sided Jacobi SVD of the accumulated triangular factor
-    ``R = U_r Sigma V^H`` whose rotation ``U_r`` is folded into the last application.  Columns of the result equal
-    the reference's ``U`` up to sign (rotations inside clustered singular subspaces).  ``truncation_tol > 0``
-    drops directions with ``sigma_j <= tol * sigma_0`` (default 0 keeps all r, like the reference).
-    """
+    CholeskyQR3 for cond(S) >~ 1e8).  The last pass is NOT applied: the caller folds ``rinv`` into the rotation."""
     lib = _ffi.load()
     _check_mat(s, "s")
     dev = s.device
@@ -354,26 +373,91 @@ def orthonormalize(s: torch.Tensor, truncation_tol: float = 0.0, group=None, n_g
         r_tot = gw if r_tot is None else gemm_nn(gw, r_tot)
         final = (departure < 0.1 and shift == 0.0) or p == max_passes - 1
         if final:
-            u = torch.empty((r, r), dtype=C128, device=dev)
-            sigma = torch.empty(r, dtype=torch.float64, device=dev)
-            sweeps = torch.zeros(1, dtype=torch.int32, device=dev)
-            nbytes = lib.mf_jacobi_svd_ws_bytes(r)
-            ws = workspaces.get("jacobi", nbytes, dev)
-            with _timed("jacobi_svd"):
-                _ffi.check(lib.mf_jacobi_svd_c128(_ptr(r_tot), r_tot.stride(0), r, _ptr(u), u.stride(0), _ptr(sigma), 40, 4.0 * eps,
-                                                  _ptr(sweeps), _ptr(ws), ws.numel(), _stream()), "mf_jacobi_svd_c128")
-            sig = sigma.cpu().numpy()
-            keep = r
-            if truncation_tol > 0.0 and sig[0] > 0.0:
-                keep = max(1, int(np.count_nonzero(sig > truncation_tol * sig[0])))
-            w = gemm_nn(rinv, u[:, :keep] if keep < r else u)
-            q = gemm_nn(x, w)
-            return q, BasisInfo(sig, p + 1, shifts, int(sweeps.item()), keep)
+            return CholQR(x, r_tot, rinv, p + 1, shifts)
         tgt = p % 2
         if bufs[tgt] is None:
             bufs[tgt] = torch.empty((n_loc, r), dtype=C128, device=dev)
         x = gemm_nn(x, rinv, out=bufs[tgt])
     raise AssertionError("unreachable")
+
+
+def basis_rotation(cq: CholQR, truncation_tol: float = 0.0) -> tuple[torch.Tensor, BasisInfo]:
+    """One-sided Jacobi SVD of the accumulated triangular factor ``r_tot = U_r Sigma V^H``; returns
+    ``w = rinv @ U_r[:, :keep]`` so that the basis is ``q = x @ w`` (columns ordered like the left singular vectors
+    of the snapshot block, ``truncation_tol > 0`` drops directions with ``sigma_j <= tol * sigma_0``)."""
+    lib = _ffi.load()
+    r_tot = cq.r_tot
+    dev = r_tot.device
+    r = r_tot.shape[0]
+    eps = np.finfo(np.float64).eps
+    u = torch.empty((r, r), dtype=C128, device=dev)
+    sigma = torch.empty(r, dtype=torch.float64, device=dev)
+    sweeps = torch.zeros(1, dtype=torch.int32, device=dev)
+    nbytes = lib.mf_jacobi_svd_ws_bytes(r)
+    ws = workspaces.get("jacobi", nbytes, dev)
+    r_work = r_tot.clone()           # the SVD destroys its input; keep r_tot (S = x r_tot) for the caller
+    with _timed("jacobi_svd"):
+        _ffi.check(lib.mf_jacobi_svd_c128(_ptr(r_work), r_work.stride(0), r, _ptr(u), u.stride(0), _ptr(sigma), 40, 4.0 * eps,
+                                          _ptr(sweeps), _ptr(ws), ws.numel(), _stream()), "mf_jacobi_svd_c128")
+    keep = r
+    if truncation_tol > 0.0:
+        sig = sigma.cpu().numpy()
+        if sig[0] > 0.0:
+            keep = max(1, int(np.count_nonzero(sig > truncation_tol * sig[0])))
+    w = gemm_nn(cq.rinv, u[:, :keep] if keep < r else u)
+    return w, BasisInfo(sigma, cq.passes, cq.shifts, sweeps, keep)
+
+
+def orthonormalize(s: torch.Tensor, truncation_tol: float = 0.0, group=None, n_global: Optional[int] = None,
+                   max_passes: int = 6) -> tuple[torch.Tensor, BasisInfo]:
+    """Orthonormal basis of span(S) with columns ordered like the left singular vectors of S.
+
+    B200 replacement of ``np.linalg.svd(S, full_matrices=False)[0]`` (implementation.py:226/298/210):
+    ``cholesky_qr`` (CholeskyQR2 / shifted CholeskyQR3), then ``basis_rotation`` (SVD of the small triangular
+    factor) whose rotation is folded into the last application ``q = x @ w``.  Columns of the result equal the
+    reference's ``U`` up to sign (rotations inside clustered singular subspaces).  ``truncation_tol > 0`` drops
+    directions with ``sigma_j <= tol * sigma_0`` (default 0 keeps all r, like the reference).
+    """
+    cq = cholesky_qr(s, group=group, max_passes=max_passes)
+    w, info = basis_rotation(cq, truncation_tol)
+    q = gemm_nn(cq.x, w)
+    return q, info
+
+
+_side_streams = {}
+
+
+def basis_and_projection(s: torch.Tensor, project_block, group=None, truncation_tol: float = 0.0):
+    """Stages 1 + 2 with the small-matrix work taken off the critical path.
+
+    ``project_block(x)`` must return ``(g_list, bt)``: the (all-reduced) r x r products ``x^T (A_i x)`` for every
+    operator (``None`` for zero operators) and ``x^T b``, for the UN-ROTATED Cholesky-QR block ``x``.  Because the
+    basis is ``q = x w`` with a small r x r' matrix ``w`` (inverse triangular factor times the SVD rotation),
+    ``q^T A q = w^T (x^T A x) w``: the SpMMs and the long contractions do not wait for the Jacobi SVD, which runs
+    (with ``q = x w`` itself) on a side stream concurrently with them.  Returns ``(q, [a_i_r], b_r, BasisInfo)``.
+    """
+    dev = s.device
+    cq = cholesky_qr(s, group=group)
+    main = torch.cuda.current_stream()
+    side = _side_streams.get(str(dev))
+    if side is None:
+        side = _side_streams[str(dev)] = torch.cuda.Stream(device=dev)
+    ev0 = torch.cuda.Event()
+    ev0.record(main)
+    g_list, bt = project_block(cq.x)                     # queued on the main stream
+    side.wait_event(ev0)
+    with torch.cuda.stream(side):
+        w, info = basis_rotation(cq, truncation_tol)
+        q = gemm_nn(cq.x, w)
+        ev1 = torch.cuda.Event()
+        ev1.record(side)
+    main.wait_event(ev1)
+    for t in (w, q, info._sigma, info._sweeps):
+        if isinstance(t, torch.Tensor):
+            t.record_stream(main)
+    reduced = [None if g is None else gemm_nn(gemm_tn(w, g, conj=False), w) for g in g_list]
+    b_r = gemm_tn(w, bt, conj=False)
+    return q, reduced, b_r, info
 
 
 # ------------------------------------------------------------------------------------------- stages 3 + 4

@@ -195,20 +195,23 @@ class ShardedHotPath:
         group = self.group if self.world > 1 else None
         ev = [] if self.stage_events is not None else None
         self._mark(ev)
-        q, info = dv.orthonormalize(s_local, group=group)
-        self._mark(ev)
-        reduced = []
-        for csr, plan in zip(self.ops, self.plans):
-            if csr is None:
-                reduced.append(None)
-                continue
-            if self.world > 1:
-                self._win = exchange_halo(q, plan, self._win, group)
-                y = dv.spmm(csr, self._win[:plan.win1 - plan.win0])
-            else:
-                y = dv.spmm(csr, q)
-            reduced.append(allreduce_sum_(dv.gemm_tn(y, q, conj=False), group))
-        b_r = allreduce_sum_(dv.project_rhs(self.b, q, self.row0, conj=False), group)
+        def project_block(x):
+            """x^T (A_i x) and x^T b for the un-rotated Cholesky-QR block (row partials all-reduced)."""
+            g_list = []
+            for csr, plan in zip(self.ops, self.plans):
+                if csr is None:
+                    g_list.append(None)
+                    continue
+                if self.world > 1:
+                    self._win = exchange_halo(x, plan, self._win, group)
+                    y = dv.spmm(csr, self._win[:plan.win1 - plan.win0])
+                else:
+                    y = dv.spmm(csr, x)
+                g_list.append(allreduce_sum_(dv.gemm_tn(y, x, conj=False), group))
+            bt = allreduce_sum_(dv.project_rhs(self.b, x, self.row0, conj=False), group)
+            return g_list, bt
+
+        q, reduced, b_r, info = dv.basis_and_projection(s_local, project_block, group=group)
         sym = [None if o is None else dv.symmetrize(o) for o in reduced]
         c0, c1, c2, cb, zs = self.coeffs
         self._mark(ev)

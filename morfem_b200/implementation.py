@@ -139,6 +139,12 @@ class _DeviceOperators:
             self._a[i] = self.dv.csr_of_transpose(csc_array(a.T if issparse(a) else np.asarray(a).T), self.dev)
         return self._a[i]
 
+    def project_block(self, x):
+        """``x^T (a_i x)`` for every operator and ``x^T b`` -- the callback of ``device.basis_and_projection``."""
+        dv = self.dv
+        g_list = [None if z else dv.gemm_tn(dv.spmm(at, x), x, conj=False) for at, z in zip(self.at, self.zero)]
+        return g_list, dv.project_rhs(self.b, x, 0, conj=False)
+
     def project(self, q):
         """Stage 2 (implementation.py:180-184): returns device (a0_r, a1_r, a2_r, b_r); zero operators give zeros."""
         dv = self.dv
@@ -286,9 +292,9 @@ def morfem_from_snapshots(snapshots: np.ndarray, domain: np.ndarray, a0: csc_arr
     its full-order SuperLU solves, i.e. exactly the path the north star puts on the GPU."""
     from . import device as dv
     md = ModelDefinition(domain, a0, a1, a2, b, t_a0, t_a1, t_a2, t_b)
-    qd, _ = dv.orthonormalize(dv.real_or_complex_to_device(snapshots), truncation_tol=TRUNCATION_TOL)
     ops = _DeviceOperators(md)
-    a0_r, a1_r, a2_r, b_r = ops.project(qd)
+    qd, (a0_r, a1_r, a2_r), b_r, _ = dv.basis_and_projection(dv.real_or_complex_to_device(snapshots), ops.project_block,
+                                                             truncation_tol=TRUNCATION_TOL)
     res = _sweep_device(domain, [a0_r, a1_r, a2_r], b_r, t_a0, t_a1, t_a2, t_b, want_x=True, want_gsm=False)
     _warn_singular(res.info.cpu().numpy())
     real = _real_inputs(a0, a1, a2, b) and not np.iscomplexobj(snapshots)

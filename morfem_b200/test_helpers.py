@@ -119,9 +119,9 @@ def model_order_reduction_gsm_from_snapshots(frequency_points, snapshots, in_c, 
     frequency_points = np.asarray(frequency_points, dtype=np.float64)
     md = ModelDefinition(frequency_points, in_c, csc_array(in_c.shape), in_gamma, in_b, lambda t: 1., lambda t: t, lambda t: t ** 2,
                          lambda t: b_coefficient(t))
-    qd, _ = dv.orthonormalize(dv.real_or_complex_to_device(snapshots), truncation_tol=impl.TRUNCATION_TOL)
     ops = impl._DeviceOperators(md)
-    a0_r, a1_r, a2_r, b_r = ops.project(qd)
+    _, (a0_r, a1_r, a2_r), b_r, _ = dv.basis_and_projection(dv.real_or_complex_to_device(snapshots), ops.project_block,
+                                                            truncation_tol=impl.TRUNCATION_TOL)
     res = impl._sweep_device(frequency_points, [a0_r, a1_r, a2_r], b_r, md.t_a0, md.t_a1, md.t_a2, md.t_b, want_x=False, want_gsm=True)
     gsm = dv.download(res.gsm, pinned_out)
     impl._warn_singular(dv.download(res.info))
