@@ -41,64 +41,95 @@ __global__ void equilibrate_kernel(cplx* G, long long ld, int r, double shift, d
 // (r <= POTRF_SMEM_MAX): every step of the factorisation is a dependent access, which costs an L2 round trip each
 // when the matrix stays in global memory.
 constexpr int POTRF_SMEM_MAX = 112;
+constexpr int POTRF_THREADS = 256;
 template <bool SMEM>
-__global__ void __launch_bounds__(1024) potrf_upper_kernel(cplx* Gg, long long ldg, int r, int* info) {
+__global__ void __launch_bounds__(POTRF_THREADS) potrf_upper_kernel(cplx* Gg, long long ldg, int r, int* info) {
     extern __shared__ __align__(16) cplx gsm[];
     __shared__ int bad;
     cplx* G = SMEM ? gsm : Gg;
     const long long ld = SMEM ? (long long)(r | 1) : ldg;
-    if (SMEM) for (int idx = threadIdx.x; idx < r * r; idx += blockDim.x) { int i = idx / r, j = idx - i * r; G[i * ld + j] = Gg[i * ldg + j]; }
-    if (threadIdx.x == 0) bad = 0;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = POTRF_THREADS / 32;
+    if (SMEM) for (int i = warp; i < r; i += nwarps) for (int j = lane; j < r; j += 32) G[i * ld + j] = Gg[i * ldg + j];
+    if (tid == 0) bad = 0;
     __syncthreads();
     for (int k = 0; k < r; ++k) {
-        double piv = G[k * ld + k].x;
-        if (!(piv > 0.0) || !isfinite(piv)) { if (threadIdx.x == 0) bad = k + 1; }
+        const double piv = G[k * ld + k].x;
+        if (!(piv > 0.0) || !isfinite(piv)) { if (tid == 0) bad = k + 1; }
         __syncthreads();
         if (bad) break;
-        const double rkk = sqrt(piv), inv = 1.0 / rkk;
-        for (int j = k + threadIdx.x; j < r; j += blockDim.x) {
+        const double inv = rsqrt(piv), rkk = piv * inv;
+        for (int j = k + tid; j < r; j += POTRF_THREADS) {
             cplx v = G[k * ld + j];
             if (j == k) v = cmake(rkk, 0.0); else { v.x *= inv; v.y *= inv; }
             G[k * ld + j] = v;
         }
         __syncthreads();
-        const int w = r - (k + 1);
-        for (int idx = threadIdx.x; idx < w * w; idx += blockDim.x) {
-            int ii = idx / w, jj = idx - ii * w;
-            if (jj < ii) continue;
-            int i = k + 1 + ii, j = k + 1 + jj;
-            cplx a = G[i * ld + j];
-            cfms(a, cconj(G[k * ld + i]), G[k * ld + j]);
-            G[i * ld + j] = a;
+        // trailing update of the upper triangle: one row per warp, lanes along the row
+        for (int i = k + 1 + warp; i < r; i += nwarps) {
+            const cplx gki = cconj(G[k * ld + i]);
+            for (int j = i + lane; j < r; j += 32) {
+                cplx a = G[i * ld + j];
+                cfms(a, gki, G[k * ld + j]);
+                G[i * ld + j] = a;
+            }
         }
         __syncthreads();
     }
-    for (int idx = threadIdx.x; idx < r * r; idx += blockDim.x) {
-        int i = idx / r, j = idx - i * r;
-        Gg[i * ldg + j] = (j < i) ? cmake(0.0, 0.0) : G[i * ld + j];
-    }
-    if (threadIdx.x == 0 && info) *info = bad;
+    for (int i = warp; i < r; i += nwarps)
+        for (int j = lane; j < r; j += 32) Gg[i * ldg + j] = (j < i) ? cmake(0.0, 0.0) : G[i * ld + j];
+    if (tid == 0 && info) *info = bad;
 }
 
 // ------------------------------------------------------------------------------------------------- trtri
-// One warp per column j of Rinv: back substitution R x = e_j; x kept in shared memory.  With SMEM the CTA first stages
-// the leading (jmax+1) x (jmax+1) block of R it needs in shared memory (dependent reads otherwise pay L2 latency).
+// One warp per column j of Rinv = R^-1 (R x = e_j).
+//   SMEM (r <= 96): the CTA stages the block of R it needs and the reciprocal diagonal in shared memory; the warp keeps
+//   x in registers (row i in lane i % 32, slot i / 32) and sweeps k = j .. 0: x_k <- x_k / r_kk, broadcast by shuffle,
+//   then every lane updates its own rows -- no reduction on the dependent chain.
+//   otherwise: dot-product form on global memory.
 constexpr int TRTRI_SMEM_MAX = 96;
 template <bool SMEM>
 __global__ void trtri_upper_kernel(const cplx* __restrict__ Rg, long long ldg, int r, cplx* __restrict__ Rinv, long long ldi) {
     extern __shared__ __align__(16) cplx xs_all[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
     const int j = blockIdx.x * wpb + warp;
-    const cplx* R = Rg; long long ldr = ldg;
     if (SMEM) {
-        cplx* Rs = xs_all + (size_t)wpb * r;
+        constexpr int SL = (TRTRI_SMEM_MAX + 31) / 32;
+        cplx* Rs = xs_all;                                  // n x lds
         const int jmax = min(r - 1, (int)(blockIdx.x * wpb + wpb - 1)), n = jmax + 1;
         const int lds = r | 1;
-        for (int idx = threadIdx.x; idx < n * n; idx += blockDim.x) { int i = idx / n, k = idx - i * n; if (k >= i) Rs[i * lds + k] = Rg[i * ldg + k]; }
+        cplx* rd = Rs + (size_t)n * lds;                    // reciprocal diagonal
+        for (int i = warp; i < n; i += wpb) for (int k = i + lane; k < n; k += 32) Rs[i * lds + k] = Rg[i * ldg + k];
+        for (int i = threadIdx.x; i < n; i += blockDim.x) rd[i] = crecip(Rg[i * ldg + i]);
         __syncthreads();
-        R = Rs; ldr = lds;
+        if (j >= r) return;
+        double xr[SL], xi[SL];
+#pragma unroll
+        for (int s = 0; s < SL; ++s) { xr[s] = (s * 32 + lane == j) ? 1.0 : 0.0; xi[s] = 0.0; }
+#pragma unroll
+        for (int ks = SL - 1; ks >= 0; --ks) {
+            for (int kl = 31; kl >= 0; --kl) {
+                const int k = ks * 32 + kl;
+                if (k > j) continue;
+                const cplx xk0 = cmul(cmake(xr[ks], xi[ks]), rd[k]);
+                const double xkr = __shfl_sync(0xffffffffu, xk0.x, kl), xki = __shfl_sync(0xffffffffu, xk0.y, kl);
+                if (lane == kl) { xr[ks] = xkr; xi[ks] = xki; }
+#pragma unroll
+                for (int s = 0; s <= ks; ++s) {
+                    const int i = s * 32 + lane;
+                    if (i < k) {
+                        const cplx u = Rs[i * lds + k];
+                        xr[s] = fma(-u.x, xkr, xr[s]); xr[s] = fma(u.y, xki, xr[s]);
+                        xi[s] = fma(-u.x, xki, xi[s]); xi[s] = fma(-u.y, xkr, xi[s]);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int s = 0; s < SL; ++s) { const int i = s * 32 + lane; if (i < r) Rinv[i * ldi + j] = (i <= j) ? cmake(xr[s], xi[s]) : cmake(0.0, 0.0); }
+        return;
     }
     if (j >= r) return;
+    const cplx* R = Rg; const long long ldr = ldg;
     cplx* x = xs_all + (size_t)warp * r;
     if (lane == 0) x[j] = crecip(R[j * ldr + j]);
     __syncwarp();
@@ -351,9 +382,9 @@ extern "C" int mf_potrf_upper_c128(mf_c128* G, int64_t ld, int r, int* info, voi
     if (r <= POTRF_SMEM_MAX) {
         const size_t smem = sizeof(cplx) * (size_t)r * (r | 1);
         MF_CHECK_CUDA(cudaFuncSetAttribute(potrf_upper_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        potrf_upper_kernel<true><<<1, 1024, smem, (cudaStream_t)stream>>>((cplx*)G, ld, r, info);
+        potrf_upper_kernel<true><<<1, POTRF_THREADS, smem, (cudaStream_t)stream>>>((cplx*)G, ld, r, info);
     } else {
-        potrf_upper_kernel<false><<<1, 1024, 0, (cudaStream_t)stream>>>((cplx*)G, ld, r, info);
+        potrf_upper_kernel<false><<<1, POTRF_THREADS, 0, (cudaStream_t)stream>>>((cplx*)G, ld, r, info);
     }
     MF_CHECK_LAUNCH();
     return 0;
@@ -366,7 +397,7 @@ extern "C" int mf_trtri_upper_c128(const mf_c128* R, int64_t ldr, int r, mf_c128
     if ((const void*)R == (const void*)Rinv) MF_FAIL_ARG(4, "Rinv must not alias R");
     const int wpb = 4;
     if (r <= TRTRI_SMEM_MAX) {
-        const size_t smem = sizeof(cplx) * ((size_t)wpb * r + (size_t)r * (r | 1));
+        const size_t smem = sizeof(cplx) * ((size_t)r * (r | 1) + (size_t)r);
         MF_CHECK_CUDA(cudaFuncSetAttribute(trtri_upper_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         trtri_upper_kernel<true><<<(r + wpb - 1) / wpb, wpb * 32, smem, (cudaStream_t)stream>>>((const cplx*)R, ldr, r, (cplx*)Rinv, ldi);
     } else {
