@@ -257,6 +257,11 @@ def run_b200(args, wl, rank, world, local_rank):
         all_ms += a["ms"]
         if a["ms"] > dom_ms:
             dominant, dom_ms = name, a["ms"]
+    traffic = {}
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+    except Exception:
+        pass
     roof = None
     if dominant is not None:
         a = agg[dominant]
@@ -267,11 +272,12 @@ def run_b200(args, wl, rank, world, local_rank):
         if t_flop >= t_mem:
             ach = a["flops"] / a["calls"] / (ms_call * 1e-3) / 1e12
             roof = {"kernel": dominant, "bound": "tensor", "achieved": ach, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": ach / FP64_PEAK_TFLOPS,
-                    "traffic": None, "peak_source": "FP64 tensor-pipe (DMMA) peak measured on this pool's B200 by tools/fp64_peaks.cu; "
+                    "traffic": (traffic.get(dominant) or {}).get("bytes") if args.workload == "cfg2" else None, "peak_source": "FP64 tensor-pipe (DMMA) peak measured on this pool's B200 by tools/fp64_peaks.cu; "
                                                     "MEASURED_PEAKS.json holds no FP64 figure and its bf16 figure does not bound an FP64 kernel", **share}
         else:
             ach = a["bytes"] / a["calls"] / (ms_call * 1e-3) / 1e9
-            roof = {"kernel": dominant, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None,
+            roof = {"kernel": dominant, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
+                    "traffic": (traffic.get(dominant) or {}).get("bytes") if args.workload == "cfg2" else None,
                     "peak_source": peak_src, **share}
 
     # ---- end to end through the reference-facing call, host (pinned) buffers in, host array out (rank-local job)

@@ -192,3 +192,55 @@ def test_public_api_greedy_driver_matches_live_reference(dv):
     # both ROMs stop at the same 1e-6 residual threshold; they agree with each other and with the full-order sweep
     # to the accuracy the reference itself reports against its full solve (main.py:42-44, ~1e-7)
     assert err_rom.max() < 1e-5 and err_full.max() < 1e-5
+
+
+# ------------------------------------------------------------- overlapped stages 1 + 2 and the sharded driver
+def test_basis_and_projection_equals_sequential_stages(dv):
+    """``q^T A q = w^T (x^T A x) w``: the overlapped evaluation (SVD rotation on a side stream) must reproduce the
+    sequential orthonormalize -> project chain and the oracle, stage isolated on the same basis."""
+    from morfem_b200 import implementation as impl, test_helpers as th
+    g = np.load(os.path.join(GOLDEN, "stages_n600.npz"))
+    in_c, in_gamma, in_b = operators_from(g)
+    keep = 10
+    md = impl.ModelDefinition(g["f"], in_c, csc_array(in_c.shape), in_gamma, in_b, lambda t: 1.0, lambda t: t, lambda t: t ** 2, th.b_coefficient)
+    ops = impl._DeviceOperators(md)
+    sd = dv.to_device_c128(g["snapshots"][:, :keep])
+    q, reduced, b_r, info = dv.basis_and_projection(sd, ops.project_block)
+    torch.cuda.synchronize()
+    qh = q.cpu().numpy().real
+    assert np.linalg.norm(qh.T @ qh - np.eye(keep)) < 1e-12
+    assert reduced[1] is None and info.kept == keep and info.passes >= 2
+    ref = orc.galerkin_projection(qh, in_c, md.a1, in_gamma, in_b)          # implementation.py:180-184 on the SAME q
+    for new, old in ((reduced[0], ref[0]), (reduced[2], ref[2]), (b_r, ref[3])):
+        assert orc.rel_err(new.cpu().numpy(), old) < 1e-10
+    seq = ops.project(q)
+    for new, old in ((reduced[0], seq[0]), (reduced[2], seq[2]), (b_r, seq[3])):
+        assert orc.rel_err(new.cpu().numpy(), old.cpu().numpy()) < 1e-10
+    sig = np.linalg.svd(g["snapshots"][:, :keep], compute_uv=False)
+    assert np.max(np.abs(info.sigma - sig)) < 1e-12 * sig[0]
+
+
+def test_sharded_hot_path_single_rank_matches_oracle(dv):
+    """``dist.ShardedHotPath`` (the call bench.py times) on one rank: S-parameters against the oracle's chained path."""
+    from morfem_b200 import dist as mfd
+    from scipy.constants import pi, epsilon_0
+    nx, ny, nz = 6, 5, 60
+    ct, tt = synthetic.waveguide_operators(nx, ny, nz)
+    n = ct.shape[0]
+    wp = synthetic.port_matrix(n, 2, 19)
+    in_c, in_gamma, in_b = synthetic.driver_scaled(ct, tt, wp)
+    f = synthetic.frequency_points(64)
+    s = synthetic.snapshot_matrix(n, 12, seed=3, decay_decades=4.0)
+    cb = np.array([orc.b_coefficient(t) for t in f])
+    path = mfd.ShardedHotPath([in_c, csc_array(in_c.shape), in_gamma], in_b, n, f.size, [np.ones_like(f), f, f ** 2, cb, 2 * pi * f * epsilon_0])
+    gsm, q, (a0_r, a1_r, a2_r, b_r), res = path.step(dv.to_device_c128(s), want_x=True)
+    torch.cuda.synchronize()
+    qh = q.cpu().numpy().real
+    ref = orc.galerkin_projection(qh, in_c, csc_array(in_c.shape), in_gamma, in_b)
+    x_ref = orc.reduced_sweep(f, ref[0], ref[1], ref[2], ref[3], lambda t: 1.0, lambda t: t, lambda t: t ** 2, orc.b_coefficient)
+    s_ref = orc.scattering_sweep(f, x_ref, ref[3])
+    cond = np.array([np.linalg.cond(orc.system_matrix(1.0, t, t ** 2, ref[0], ref[1], ref[2])) for t in f])
+    tol = np.maximum(1e-10, 50 * np.finfo(float).eps * cond)
+    err = np.linalg.norm((gsm.cpu().numpy() - s_ref).reshape(f.size, -1), axis=1) / np.linalg.norm(s_ref.reshape(f.size, -1), axis=1)
+    assert np.all(err < tol), (err.max(), tol.max())
+    assert not np.any(res.info.cpu().numpy())

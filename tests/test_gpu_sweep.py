@@ -68,8 +68,8 @@ def test_sweep_matches_live_reference_fixture(dv, name):
         assert np.all(es < tol), (name, variant, es.max(), tol.max())
 
 
-@pytest.mark.parametrize("r,m,nf", [(1, 1, 3), (2, 2, 5), (7, 3, 33), (16, 16, 9), (31, 5, 40), (48, 2, 300), (100, 8, 12), (128, 4, 20),
-                                    (200, 2, 6)])
+@pytest.mark.parametrize("r,m,nf", [(1, 1, 3), (2, 2, 5), (7, 3, 33), (16, 16, 9), (31, 5, 40), (48, 2, 300), (100, 8, 12), (112, 16, 5),
+                                    (113, 1, 4), (128, 4, 20), (200, 2, 6), (257, 9, 3), (384, 16, 2), (512, 4, 150)])
 def test_sweep_matches_oracle_on_seeded_models(dv, r, m, nf):
     from morfem_b200 import synthetic
     a0, a1, a2, b = synthetic.reduced_model(r, m, seed=100 + r)
@@ -134,6 +134,27 @@ def test_sweep_reports_singular_points_like_lu_factor(dv):
     for variant in [0] + variants_for(dv, r, m):
         res = run_sweep(dv, f, a0, None, None, b, np.ones(3), variant=variant, want_gsm=False)
         assert list(res.info.cpu().numpy()) == [4, 4, 4]
+
+
+def test_sweep_singular_and_pivoting_in_the_streamed_kernel(dv):
+    """r > 112 runs the streamed two-level kernel: a permutation-like matrix needs exchanges in every outer panel, and an
+    exactly singular matrix must report the first zero pivot (here deep inside the third outer panel)."""
+    r, m = 150, 2
+    rng = np.random.default_rng(8)
+    a0 = np.fliplr(np.eye(r)) * 2.0 + 1e-3 * rng.standard_normal((r, r))
+    a0 = (a0 + a0.T) / 2
+    b = rng.standard_normal((r, m))
+    f = np.array([3e9, 4e9, 5e9])
+    zero = np.zeros((r, r))
+    x_ref = orc.reduced_sweep(f, a0, zero, zero, b, lambda t: 1.0, lambda t: t, lambda t: t ** 2, lambda t: 1.0)
+    for variant in [0] + variants_for(dv, r, m):
+        res = run_sweep(dv, f, a0, None, None, b, np.ones(3), variant=variant)
+        assert np.all(per_point_rel(res.x.cpu().numpy().real, x_ref) < 1e-11), variant
+    sing = np.eye(r)
+    sing[77, 77] = 0.0
+    for variant in [0] + variants_for(dv, r, m):
+        res = run_sweep(dv, f, sing, None, None, np.ones((r, m)), np.ones(3), variant=variant, want_gsm=False)
+        assert list(res.info.cpu().numpy()) == [78, 78, 78], variant
 
 
 def test_sweep_outputs_are_optional_and_idempotent(dv):
