@@ -204,7 +204,11 @@ def run_b200(args, wl, rank, world, local_rank):
             dist.barrier()
             torch.cuda.synchronize()
 
+    use_graph = world == 1 and not args.no_graph
+
     def step():
+        if use_graph:
+            return path.step_graph(s_dev, want_x=False)       # whole step replayed from one CUDA graph
         return path.step(s_dev, want_x=False, gather=True)
 
     for _ in range(max(args.warmup, 3)):
@@ -222,6 +226,11 @@ def run_b200(args, wl, rank, world, local_rank):
     barrier()
     clocks = sampler.stop()
     launches = _ffi.launch_count() - launches0
+    if use_graph:
+        # a graph replay launches the captured kernels without passing through the C ABI's counter
+        launches = args.steps * path.launches_per_graph
+        if path.verify() is not None:
+            raise SystemExit("bench: optimistic CholeskyQR2 failed verification on the synthetic snapshot block")
     ms_total = e0.elapsed_time(e1)
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
     if world > 1:
@@ -235,7 +244,7 @@ def run_b200(args, wl, rank, world, local_rank):
     dv.timer = dv.KernelTimer()
     path.stage_events = []
     for _ in range(prof_steps):
-        step()
+        path.step(s_dev, want_x=False, gather=True)           # eager: per-kernel events cannot be recorded inside a replay
     agg = dv.timer.summary()
     dv.timer = None
     # basis and projection overlap (the SVD rotation runs on a side stream under the SpMMs), so they are timed together
@@ -343,7 +352,7 @@ def run_b200(args, wl, rank, world, local_rank):
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "c128", "data": "synthetic",
                 "config": {"workload": args.workload + ": " + wl["desc"], "N_dof_per_gpu": n // world, "N_dof_total": n, "r": wl["r"], "ports": wl["m"],
-                           "freq_points_total": f_total, "step": "basis (CholeskyQR2+SVD) + projection + reduced solves + S-parameters",
+                           "freq_points_total": f_total, "step": "basis (CholeskyQR2+SVD) + projection + reduced solves + S-parameters" + (", replayed from one CUDA graph" if use_graph else ""),
                            "l2": "inputs larger than L2 (snapshot block %.0f MB + operators per GPU); no flush" % (s_dev.numel() * 16 / 1e6),
                            "parallelism": "rows of Q/operators and sweep points block-sharded over %d GPU(s)" % world},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu_baseline,
@@ -365,6 +374,7 @@ def main():
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--cpu-points", type=int, default=2000, help="sweep points the CPU arm solves per step (scaled to the full axis)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="run the eager (adaptive CholeskyQR) step instead of the CUDA-graph replay at N=1")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))

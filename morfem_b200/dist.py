@@ -182,6 +182,9 @@ class ShardedHotPath:
         self.coeffs = [dv.upload(np.ascontiguousarray(c[self.f0:self.f1], dtype=np.float64), self.dev) for c in coeffs_global]
         self._win = None
         self.stage_events = None     # bench.py: set to a list to collect per-stage CUDA events
+        self._graph = None           # (CUDAGraph, static input, static outputs, pinned flag buffer) of step_graph
+        self.launches_per_graph = 0
+
 
     def _mark(self, ev):
         if ev is not None:
@@ -189,8 +192,50 @@ class ShardedHotPath:
             e.record()
             ev.append(e)
 
-    def step(self, s_local: torch.Tensor, want_x: bool = False, gather: bool = True):
-        """One pass of the hot path.  Returns (gsm_all or gsm_local, q_local, (a0_r, a1_r, a2_r, b_r), sweep result)."""
+    def step_graph(self, s_local: torch.Tensor, want_x: bool = False):
+        """``step`` replayed from a CUDA graph (single rank): the whole launch sequence -- optimistic CholeskyQR2 (two
+        passes, success flags kept on the device), SpMMs, contractions, SVD rotation on its side stream, sweep -- is
+        captured once per snapshot-block shape and replayed with one launch, which removes the host launch gaps between
+        the ~45 short kernels of a step.  Call ``verify()`` before trusting the results: if a Cholesky broke down or the
+        block needed a third pass it re-runs the adaptive ``step``.  Outputs are static tensors overwritten by the next
+        replay."""
+        if self.world > 1:
+            raise RuntimeError("step_graph is single-rank; use step() under torchrun")
+        key = (tuple(s_local.shape), bool(want_x))
+        if self._graph is None or self._graph["key"] != key:
+            static_s = s_local.clone()
+            for _ in range(2):                                   # warm-up: workspaces, function attributes, side stream
+                self.step(static_s, want_x=want_x, gather=False, optimistic=True)
+            torch.cuda.synchronize()
+            from . import _ffi
+            graph = torch.cuda.CUDAGraph()
+            launches0 = _ffi.launch_count()
+            with torch.cuda.graph(graph):
+                out = self.step(static_s, want_x=want_x, gather=False, optimistic=True)
+            self.launches_per_graph = _ffi.launch_count() - launches0     # kernels of this library inside one replay
+            flags_host = torch.empty((2, 32), dtype=torch.uint8).pin_memory()
+            self._graph = {"key": key, "graph": graph, "s": static_s, "out": out, "flags_host": flags_host, "want_x": want_x}
+        gr = self._graph
+        if s_local.data_ptr() != gr["s"].data_ptr():
+            gr["s"].copy_(s_local)
+        gr["graph"].replay()
+        gr["flags_host"].copy_(gr["out"][4].flags, non_blocking=True)
+        return gr["out"][:4]
+
+    def verify(self):
+        """Synchronise and check the deferred flags of the last ``step_graph``; on failure return the results of the
+        adaptive path instead (None when the optimistic results stand)."""
+        gr = self._graph
+        if gr is None:
+            return None
+        torch.cuda.current_stream().synchronize()
+        if self.dv.flags_ok(gr["flags_host"]):
+            return None
+        return self.step(gr["s"], want_x=gr["want_x"], gather=False)
+
+    def step(self, s_local: torch.Tensor, want_x: bool = False, gather: bool = True, optimistic: bool = False):
+        """One pass of the hot path.  Returns (gsm_all or gsm_local, q_local, (a0_r, a1_r, a2_r, b_r), sweep result)
+        (plus the BasisInfo when ``optimistic``: its ``flags`` still have to be verified, see ``step_graph``)."""
         dv = self.dv
         group = self.group if self.world > 1 else None
         ev = [] if self.stage_events is not None else None
@@ -211,7 +256,7 @@ class ShardedHotPath:
             bt = allreduce_sum_(dv.project_rhs(self.b, x, self.row0, conj=False), group)
             return g_list, bt
 
-        q, reduced, b_r, info = dv.basis_and_projection(s_local, project_block, group=group)
+        q, reduced, b_r, info = dv.basis_and_projection(s_local, project_block, group=group, optimistic=optimistic)
         sym = [None if o is None else dv.symmetrize(o) for o in reduced]
         c0, c1, c2, cb, zs = self.coeffs
         self._mark(ev)
@@ -221,4 +266,6 @@ class ShardedHotPath:
         self._mark(ev)
         if ev is not None:
             self.stage_events.append(ev)
+        if optimistic:
+            return gsm, q, (reduced[0], reduced[1], reduced[2], b_r), res, info
         return gsm, q, (reduced[0], reduced[1], reduced[2], b_r), res

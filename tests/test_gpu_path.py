@@ -244,3 +244,29 @@ def test_sharded_hot_path_single_rank_matches_oracle(dv):
     err = np.linalg.norm((gsm.cpu().numpy() - s_ref).reshape(f.size, -1), axis=1) / np.linalg.norm(s_ref.reshape(f.size, -1), axis=1)
     assert np.all(err < tol), (err.max(), tol.max())
     assert not np.any(res.info.cpu().numpy())
+
+
+def test_graph_replay_equals_eager_step_and_falls_back(dv):
+    """The CUDA-graph replay (optimistic CholeskyQR2, flags verified afterwards) gives the eager step's S-parameters;
+    an ill-conditioned block (needs a shifted third pass) fails verification and is re-run on the adaptive path."""
+    from morfem_b200 import dist as mfd
+    from scipy.constants import pi, epsilon_0
+    nx, ny, nz = 6, 5, 60
+    ct, tt = synthetic.waveguide_operators(nx, ny, nz)
+    n = ct.shape[0]
+    in_c, in_gamma, in_b = synthetic.driver_scaled(ct, tt, synthetic.port_matrix(n, 2, 19))
+    f = synthetic.frequency_points(48)
+    cb = np.array([orc.b_coefficient(t) for t in f])
+    path = mfd.ShardedHotPath([in_c, csc_array(in_c.shape), in_gamma], in_b, n, f.size, [np.ones_like(f), f, f ** 2, cb, 2 * pi * f * epsilon_0])
+    sd = dv.to_device_c128(synthetic.snapshot_matrix(n, 12, seed=3, decay_decades=4.0))
+    eager = path.step(sd, gather=False)[0].clone()
+    for _ in range(3):
+        replay = path.step_graph(sd)[0]
+    assert path.verify() is None and path.launches_per_graph > 20
+    assert orc.rel_err(replay.cpu().numpy(), eager.cpu().numpy()) < 1e-10
+    rng = np.random.default_rng(4)      # nearly collinear columns (cond ~ 1e10 even after column scaling): CholeskyQR2 is not enough
+    bad = dv.to_device_c128(np.outer(rng.standard_normal(n), np.ones(12)) + 1e-10 * rng.standard_normal((n, 12)))
+    path.step_graph(bad)
+    redo = path.verify()
+    assert redo is not None
+    assert orc.rel_err(redo[0].cpu().numpy(), path.step(bad, gather=False)[0].cpu().numpy()) < 1e-9
