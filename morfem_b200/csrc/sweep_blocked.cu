@@ -37,7 +37,7 @@ namespace {
 // lanes read reciprocal and U entries from there.  `pbuf` = two ints for the pivot position (double buffered).
 template <int SLOTS>
 __device__ __forceinline__ void panel_factor(cplx* M, const int LD, const int R, const int row0, const int lane,
-                                             int* pbuf, int* piv, int* info_sh) {
+                                          int* pbuf, int* piv, int* info_sh) {
     cplx a[SLOTS][8];
     int pos[SLOTS];
     bool act[SLOTS];                        // slot holds a real row that has not been a pivot yet

@@ -23,22 +23,21 @@ __device__ __noinline__ cplx crecip2(cplx a) {
 
 // ---- B. row exchanges + U12 = L11^-1 A12 for one trailing column c (L11 is stored negated) -----------------------
 __device__ __forceinline__ void stepb_column(cplx* M, const int LD, const int row0, const int c, const int* pv) {
-    const int cbase = c & ~7, cin = c & 7, c_lo = row0 + 8;
+    const int cbase = c & ~7, cin = c & 7;
     cplx* colp = M + row0 * LD + cbase;
-    cplx u[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) u[j] = colp[j * LD + (cin ^ swz(j))];
+    // the (few) row exchanges of this panel, in order, straight in shared memory: compact code, uniform branches
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         const int P = pv[j];
-        if (P >= c_lo) {
-            cplx* q = M + P * LD + cbase + (cin ^ swz(P & 7));
-            const cplx tmp = *q; *q = u[j]; u[j] = tmp;
-        } else {
-#pragma unroll
-            for (int q = j + 1; q < 8; ++q) if (P == row0 + q) { const cplx tmp = u[q]; u[q] = u[j]; u[j] = tmp; }
+        if (P != row0 + j) {
+            cplx* x = colp + j * LD + (cin ^ swz(j));
+            cplx* y = M + P * LD + cbase + (cin ^ swz(P & 7));
+            const cplx tmp = *x; *x = *y; *y = tmp;
         }
     }
+    cplx u[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) u[j] = colp[j * LD + (cin ^ swz(j))];
 #pragma unroll
     for (int j = 1; j < 8; ++j) {
         const cplx* lrow = M + (row0 + j) * LD + row0;
@@ -47,7 +46,7 @@ __device__ __forceinline__ void stepb_column(cplx* M, const int LD, const int ro
         for (int i = 0; i < j; ++i) cfma(u[j], lrow[i ^ sw], u[i]);
     }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) colp[j * LD + (cin ^ swz(j))] = u[j];
+    for (int j = 1; j < 8; ++j) colp[j * LD + (cin ^ swz(j))] = u[j];
 }
 
 // per-lane fragment offsets inside 8 x 8 blocks of the swizzled matrix
