@@ -251,7 +251,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) sweep_blocked_kernel(SweepParam
             }
 #pragma unroll
             for (int ks = SLOTS - 1; ks >= 0; --ks) {
-#pragma unroll
+#pragma unroll (SLOTS <= 2 ? 4 : 1)
                 for (int kq = 3; kq >= 0; --kq) {
                     const int kb8 = ks * 32 + kq * 8;                    // first row of the block
                     if (kb8 < R) {

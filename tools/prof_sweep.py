@@ -7,7 +7,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from morfem_b200 import device as dv, synthetic, implementation as impl, test_helpers as th
 
 r, m, nf, variant = (int(v) for v in sys.argv[1:5])
-reps = int(sys.argv[5]) if len(sys.argv) > 5 else 5
+reps = int(sys.argv[5]) if len(sys.argv) > 5 else 15
 a0, a1, a2, b = synthetic.reduced_model(r, m, seed=11)
 f = np.linspace(3e9, 5e9, nf)
 cb = impl.coefficient_array(th.b_coefficient, f)
@@ -18,12 +18,14 @@ args = (ops[0], ops[1], ops[2], dv.to_device_c128(b), up(np.ones_like(f)), up(f)
 for _ in range(2):
     res = dv.sweep(*args, want_x=False, want_gsm=True, variant=variant)
 torch.cuda.synchronize()
-e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-e0.record()
-for _ in range(reps):
+times = []
+for _ in range(max(reps, 1)):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
     res = dv.sweep(*args, want_x=False, want_gsm=True, variant=variant)
-e1.record()
-torch.cuda.synchronize()
-ms = e0.elapsed_time(e1) / reps
+    e1.record()
+    torch.cuda.synchronize()
+    times.append(e0.elapsed_time(e1))
+ms = float(np.median(times))
 flops = (8 / 3) * r ** 3 + 8 * r * r * m + 16 * r * r + 8 * r * m * m
-print(f"r={r} m={m} F={nf} variant={variant}: {ms:.3f} ms, {nf / ms * 1e3:.3e} pts/s, {flops * nf / ms / 1e9:.2f} TFLOP/s, info!=0: {int((res.info != 0).sum())}")
+print(f"r={r} m={m} F={nf} variant={variant}: min {min(times):.3f} / median {ms:.3f} ms, {nf / ms * 1e3:.3e} pts/s, {flops * nf / ms / 1e9:.2f} TFLOP/s, info!=0: {int((res.info != 0).sum())}")
