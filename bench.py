@@ -31,8 +31,9 @@ WORKLOADS = {
     # name: (grid nx, ny, nz per GPU), r, ports, sweep points per GPU
     "cfg2": dict(grid=(20, 10, 1000), r=64, m=2, f=10000,
                  desc="BASELINE configs[1]: synthetic curl-curl FEM N=200k DOF, r=64 basis, 2 ports, 10k freq points on 1 B200"),
-    "cfg3": dict(grid=(25, 20, 2000), r=256, m=4, f=12500,
-                 desc="BASELINE configs[2]: synthetic N=1M DOF, r=256, 4 ports, 100k freq points (12.5k per GPU at 8 GPUs)"),
+    "cfg3": dict(grid=(25, 20, 250), r=256, m=4, f=12500,
+                 desc="BASELINE configs[2]: synthetic N=1M DOF, r=256, 4 ports, 100k freq points sharded across 8 B200 "
+                      "(per GPU: 125k rows, 12.5k points; weak scaling below 8 GPUs)"),
     "small": dict(grid=(5, 4, 100), r=16, m=2, f=500, desc="smoke-sized workload"),
 }
 METRIC = "reduced-sweep freq points/sec"

@@ -80,6 +80,19 @@ int mf_jacobi_svd_c128(mf_c128* X, int64_t ld, int r, mf_c128* U, int64_t ldu, d
 int mf_spmm_csr_c128(const int32_t* rowptr, const int32_t* colidx, const void* vals, int val_is_real,
                      int64_t nrows, const mf_c128* Q, int64_t ldq, int r, mf_c128* Y, int64_t ldy, void* stream);
 
+/* Row-grouped form of the same product for real operators with sorted column indices (the FEM operators of this path):
+ * G = mf_spmm_group_size(r) consecutive rows are handled by one warp over the UNION of their columns, so that each
+ * needed Q row is loaded once per group instead of once per non-zero (the CSR kernel is bound by L1 traffic, not HBM).
+ * Build once per operator: counts[g] = union size of group g (mf_spmm_group_count); ustart = exclusive prefix sum of
+ * counts (int64, ngroups + 1 entries, caller computed); mf_spmm_group_fill writes ucols[ustart[g] + k] and
+ * uvals[(ustart[g] + k) * G + i] (coefficient of row g*G + i, 0 when absent).  Then mf_spmm_grouped_c128 == mf_spmm_csr_c128. */
+int mf_spmm_group_size(int r);
+int mf_spmm_group_count(const int32_t* rowptr, const int32_t* colidx, int64_t nrows, int G, int32_t* counts, void* stream);
+int mf_spmm_group_fill(const int32_t* rowptr, const int32_t* colidx, const double* vals, int64_t nrows, int G,
+                       const int64_t* ustart, int32_t* ucols, double* uvals, void* stream);
+int mf_spmm_grouped_c128(const int64_t* ustart, const int32_t* ucols, const double* uvals, int64_t nrows, int G,
+                         const mf_c128* Q, int64_t ldq, int r, mf_c128* Y, int64_t ldy, void* stream);
+
 /* B_r (r x m) = Q^T B (conj_q != 0: Q^H B) for B in CSC (n x m, int32 indices, real or complex values);
  * implementation.py:184 `q_t @ md.b`.  Rows outside [row0, row0 + nlocal) are skipped so that row-sharded
  * callers can all-reduce the partial results; Q points at the caller's first local row. */

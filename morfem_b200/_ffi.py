@@ -36,6 +36,11 @@ SIGNATURES = {
                                    c_void_p, c_size_t, c_void_p]),
     "mf_spmm_csr_c128": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int64, c_void_p, c_int64, c_int, c_void_p, c_int64,
                                  c_void_p]),
+    "mf_spmm_group_size": (c_int, [c_int]),
+    "mf_spmm_group_count": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p]),
+    "mf_spmm_group_fill": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "mf_spmm_grouped_c128": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_int64, c_int, c_void_p, c_int64,
+                                     c_void_p]),
     "mf_project_rhs_c128": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int64, c_int, c_int64, c_int64,
                                     c_int, c_void_p, c_int64, c_void_p]),
     "mf_symmetrize_c128": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int64, c_void_p]),

@@ -183,6 +183,8 @@ class DeviceCSR:
     nrows: int
     ncols: int
     row0: int = 0          # first global row of this slice
+    grouped: Optional[tuple] = None   # (G, ustart int64, ucols int32, uvals float64): row-grouped form (see group_rows)
+    sorted_indices: bool = False      # column indices ascending within every row (required by group_rows)
 
     @property
     def nnz(self) -> int:
@@ -213,9 +215,11 @@ def download(t: torch.Tensor, out: Optional[torch.Tensor] = None) -> np.ndarray:
     return t.cpu().numpy()
 
 
-def csr_of_transpose(a_csc, device=None, row_range=None) -> DeviceCSR:
+def csr_of_transpose(a_csc, device=None, row_range=None, col_offset: int = 0, group_for_r: Optional[int] = None) -> DeviceCSR:
     """Upload the CSR view of ``a.T`` for a scipy ``csc_array``/``csc_matrix`` ``a`` (no conversion work: the
-    three CSC arrays are reused as they are).  ``row_range=(lo, hi)`` uploads only rows lo..hi-1 of ``a.T``."""
+    three CSC arrays are reused as they are).  ``row_range=(lo, hi)`` uploads only rows lo..hi-1 of ``a.T``;
+    ``col_offset`` is subtracted from the column indices (halo-window relative indexing); ``group_for_r`` also builds
+    the row-grouped form for basis size r on the device (real operators with sorted indices only)."""
     import scipy.sparse as sp
     device = device or require_cuda()
     a = a_csc if sp.issparse(a_csc) and a_csc.format == "csc" else sp.csc_array(a_csc)
@@ -232,8 +236,35 @@ def csr_of_transpose(a_csc, device=None, row_range=None) -> DeviceCSR:
     colidx = np.ascontiguousarray(a.indices[s:e], dtype=np.int32)
     data = np.asarray(a.data[s:e])
     vals = np.ascontiguousarray(data, dtype=np.complex128 if np.iscomplexobj(data) else np.float64)
-    return DeviceCSR(upload(np.ascontiguousarray(rowptr), device), upload(colidx, device), upload(vals, device),
-                     hi - lo, a.shape[0], lo)
+    if col_offset:
+        colidx = colidx - np.int32(col_offset)
+    csr = DeviceCSR(upload(np.ascontiguousarray(rowptr), device), upload(colidx, device), upload(vals, device),
+                    hi - lo, a.shape[0], lo, None, bool(a.has_sorted_indices))
+    if group_for_r is not None:
+        group_rows(csr, group_for_r)
+    return csr
+
+
+def group_rows(a: DeviceCSR, r: int) -> None:
+    """Build the row-grouped form of a real CSR operand with sorted column indices on the device (once per operator and
+    group size): G = mf_spmm_group_size(r) consecutive rows share one column-union list, so the SpMM loads each needed
+    Q row once per group.  No-op when already built for this G or when the values are complex."""
+    lib = _ffi.load()
+    g = int(lib.mf_spmm_group_size(r))
+    if not a.is_real or not a.sorted_indices or a.nrows == 0 or (a.grouped is not None and a.grouped[0] == g):
+        return
+    dev = a.colidx.device
+    ngroups = (a.nrows + g - 1) // g
+    counts = torch.empty(ngroups, dtype=torch.int32, device=dev)
+    _ffi.check(lib.mf_spmm_group_count(_ptr(a.rowptr), _ptr(a.colidx), a.nrows, g, _ptr(counts), _stream()), "mf_spmm_group_count")
+    ustart = torch.zeros(ngroups + 1, dtype=torch.int64, device=dev)
+    torch.cumsum(counts, 0, out=ustart[1:])
+    total = int(ustart[-1].item())
+    ucols = torch.empty(total, dtype=torch.int32, device=dev)
+    uvals = torch.empty(total * g, dtype=torch.float64, device=dev)
+    _ffi.check(lib.mf_spmm_group_fill(_ptr(a.rowptr), _ptr(a.colidx), _ptr(a.vals), a.nrows, g, _ptr(ustart), _ptr(ucols), _ptr(uvals),
+                                      _stream()), "mf_spmm_group_fill")
+    a.grouped = (g, ustart, ucols, uvals)
 
 
 def spmm(a: DeviceCSR, q: torch.Tensor, out: Optional[torch.Tensor] = None, col_offset: int = 0) -> torch.Tensor:
@@ -243,6 +274,13 @@ def spmm(a: DeviceCSR, q: torch.Tensor, out: Optional[torch.Tensor] = None, col_
     r = q.shape[1]
     if out is None:
         out = torch.empty((a.nrows, r), dtype=C128, device=q.device)
+    if a.grouped is not None and col_offset == 0 and a.grouped[0] == int(lib.mf_spmm_group_size(r)):
+        g, ustart, ucols, uvals = a.grouped
+        nbytes = ucols.numel() * (4.0 + 8.0 * g) + 8.0 * ustart.numel() + 16.0 * r * (a.nrows + q.shape[0])
+        with _timed("spmm_csr", nbytes=nbytes, flops=4.0 * a.nnz * r):
+            _ffi.check(lib.mf_spmm_grouped_c128(_ptr(ustart), _ptr(ucols), _ptr(uvals), a.nrows, g, _ptr(q), q.stride(0), r,
+                                                _ptr(out), out.stride(0), _stream()), "mf_spmm_grouped_c128")
+        return out
     colidx = a.colidx if col_offset == 0 else a.colidx - col_offset
     valb = 8.0 if a.is_real else 16.0
     with _timed("spmm_csr", nbytes=a.nnz * (valb + 4.0) + 4.0 * (a.nrows + 1) + 16.0 * r * (a.nrows + q.shape[0]),

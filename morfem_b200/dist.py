@@ -173,9 +173,7 @@ class ShardedHotPath:
             window = column_window(np.asarray(a.indptr), np.asarray(a.indices), self.row0, self.row1, a.shape[0])
             windows = gather_windows(window, group) if self.world > 1 else [window]
             plan = build_halo_plan(self.rank, self.world, n_rows, windows)
-            csr = dv.csr_of_transpose(a, self.dev, row_range=(self.row0, self.row1))
-            if plan.win0:
-                csr.colidx = csr.colidx - plan.win0          # window-relative column indices, computed once
+            csr = dv.csr_of_transpose(a, self.dev, row_range=(self.row0, self.row1), col_offset=plan.win0)   # window-relative columns
             self.ops.append(csr)
             self.plans.append(plan)
         self.b = dv.csc_to_device(b, self.dev)
@@ -247,6 +245,7 @@ class ShardedHotPath:
                 if csr is None:
                     g_list.append(None)
                     continue
+                dv.group_rows(csr, x.shape[1])       # row-grouped operand, built once per operator on first use
                 if self.world > 1:
                     self._win = exchange_halo(x, plan, self._win, group)
                     y = dv.spmm(csr, self._win[:plan.win1 - plan.win0])

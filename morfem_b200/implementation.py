@@ -142,6 +142,9 @@ class _DeviceOperators:
     def project_block(self, x):
         """``x^T (a_i x)`` for every operator and ``x^T b`` -- the callback of ``device.basis_and_projection``."""
         dv = self.dv
+        for at in self.at:
+            if at is not None:
+                dv.group_rows(at, x.shape[1])
         g_list = [None if z else dv.gemm_tn(dv.spmm(at, x), x, conj=False) for at, z in zip(self.at, self.zero)]
         return g_list, dv.project_rhs(self.b, x, 0, conj=False)
 

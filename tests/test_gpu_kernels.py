@@ -163,3 +163,28 @@ def test_project_rhs(dv, conj):
     p0 = dv.project_rhs(bd, dv.to_device_c128(q[:500]), 0, conj=conj).cpu().numpy()
     p1 = dv.project_rhs(bd, dv.to_device_c128(q[500:]), 500, conj=conj).cpu().numpy()
     assert rel(p0 + p1, ref) < 1e-14
+
+
+@pytest.mark.parametrize("r", [5, 32, 64, 100, 130, 300])
+def test_spmm_row_grouped_matches_csr_kernel(dv, r):
+    """The row-grouped SpMM (column unions of 4 / 2 consecutive rows) against scipy and against the CSR kernel, on a FEM
+    operator, on a matrix with empty and very long rows, and on a row count that is not a multiple of the group size."""
+    import scipy.sparse as sp
+    from morfem_b200 import synthetic
+    ct, _ = synthetic.waveguide_operators(5, 4, 37)
+    rng = np.random.default_rng(r)
+    rnd = sp.random(301, 301, density=0.03, random_state=3, format="csc")
+    rnd = sp.csc_array(rnd + sp.csc_array((np.ones(301), (np.zeros(301, dtype=int), np.arange(301))), shape=(301, 301)))   # one full row of a^T
+    rnd.sort_indices()
+    for a in (ct, rnd):
+        n = a.shape[0]
+        q = rng.standard_normal((n, r)) + 1j * rng.standard_normal((n, r))
+        qd = dv.to_device_c128(q)
+        csr = dv.csr_of_transpose(a)
+        y_csr = dv.spmm(csr, qd).cpu().numpy()
+        dv.group_rows(csr, r)
+        assert csr.grouped is not None and csr.grouped[0] == (4 if r <= 128 else 2)
+        y_grp = dv.spmm(csr, qd).cpu().numpy()
+        ref = (q.T @ a).T                                   # implementation.py:181: q_t @ a
+        assert rel(y_grp, ref) < 1e-14
+        assert rel(y_grp, y_csr) < 1e-14
