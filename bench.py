@@ -196,7 +196,8 @@ def run_b200(args, wl, rank, world, local_rank):
     cb = impl.coefficient_array(th.b_coefficient, f)
     coeffs = [np.ones_like(f), f, f ** 2, cb, 2 * pi * f * epsilon_0]
     path = mfd.ShardedHotPath([in_c, csc_array(in_c.shape), in_gamma], in_b, n, f.size, coeffs)
-    s_dev = dv.real_or_complex_to_device(s_loc, dev)
+    real = args.dtype == "f64"
+    s_dev = dv.real_or_complex_to_device(s_loc, dev, widen=not real)      # c128 (north star) unless --dtype f64
     f_total = f.size
 
     def barrier():
@@ -308,12 +309,12 @@ def run_b200(args, wl, rank, world, local_rank):
         out_pinned = torch.empty((f_total, wl["m"], wl["m"]), dtype=torch.complex128).pin_memory()
         k_e2e = max(3, min(args.steps, 10))
         for _ in range(2):
-            th.model_order_reduction_gsm_from_snapshots(f, s_host, c_host, g_host, b_host, pinned_out=out_pinned)
+            th.model_order_reduction_gsm_from_snapshots(f, s_host, c_host, g_host, b_host, pinned_out=out_pinned, real_path=real)
         torch.cuda.synchronize()
         dv.transfer_bytes["h2d"] = dv.transfer_bytes["d2h"] = 0
         t0 = time.perf_counter()
         for _ in range(k_e2e):
-            gsm_host = th.model_order_reduction_gsm_from_snapshots(f, s_host, c_host, g_host, b_host, pinned_out=out_pinned)
+            gsm_host = th.model_order_reduction_gsm_from_snapshots(f, s_host, c_host, g_host, b_host, pinned_out=out_pinned, real_path=real)
         torch.cuda.synchronize()
         dt = (time.perf_counter() - t0) / k_e2e
         e2e = {"value": f_total / dt, "unit": UNIT, "h2d_bytes_per_step": dv.transfer_bytes["h2d"] // k_e2e,
@@ -332,7 +333,9 @@ def run_b200(args, wl, rank, world, local_rank):
         barrier()
         t0 = time.perf_counter()
         for _ in range(k_e2e):
-            sd = s_host.to(dev, non_blocking=False).to(torch.complex128)
+            sd = s_host.to(dev, non_blocking=False)
+            if not real:
+                sd = sd.to(torch.complex128)
             gsm_all = path.step(sd, want_x=False, gather=True)[0]
             out_pinned.copy_(gsm_all)
         barrier()
@@ -354,10 +357,11 @@ def run_b200(args, wl, rank, world, local_rank):
     if rank == 0:
         sweep_k = kernels.get("sweep_lu_gsm", {})
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "c128", "data": "synthetic",
+                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "c128" if not real else "f64 (stages 1+2) / c128 (sweep)", "data": "synthetic",
                 "config": {"workload": args.workload + ": " + wl["desc"], "N_dof_per_gpu": n // world, "N_dof_total": n, "r": wl["r"], "ports": wl["m"],
                            "freq_points_total": f_total, "step": "basis (CholeskyQR2+SVD) + projection + reduced solves + S-parameters" + (", replayed from one CUDA graph" if use_graph else ""),
-                           "l2": "inputs larger than L2 (snapshot block %.0f MB + operators per GPU); no flush" % (s_dev.numel() * 16 / 1e6),
+                           "l2": "inputs larger than L2 (snapshot block %.0f MB + operators per GPU); no flush" % (s_dev.numel() * s_dev.element_size() / 1e6),
                            "parallelism": "rows of Q/operators and sweep points block-sharded over %d GPU(s)" % world},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu_baseline,
                 "stages": {"basis_plus_projection_ms": stage_ms["basis_plus_projection"], "sweep_ms": stage_ms["sweep"],
@@ -378,6 +382,9 @@ def main():
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--cpu-points", type=int, default=2000, help="sweep points the CPU arm solves per step (scaled to the full axis)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dtype", default="c128", choices=["c128", "f64"],
+                    help="c128: complex128 kernels throughout (north star); f64: real float64 twins for stages 1+2 (the reference's dtype), "
+                         "complex128 sweep")
     ap.add_argument("--no-graph", action="store_true", help="run the eager (adaptive CholeskyQR) step instead of the CUDA-graph replay at N=1")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]

@@ -100,6 +100,23 @@ int mf_project_rhs_c128(const int32_t* colptr, const int32_t* rowidx, const void
                         const mf_c128* Q, int64_t ldq, int r, int64_t row0, int64_t nlocal, int conj_q,
                         mf_c128* Br, int64_t ldb, void* stream);
 
+/* ---- real float64 twins ----------------------------------------------------------------
+ * The reference's data and its whole ROM path are real float64 (main.py:21-23, implementation.py:190).  For real
+ * snapshots and operators these entries run stages 1 + 2 on 8-byte elements: half the bytes and a quarter of the flops
+ * of the complex128 entries, with results that are bit-identical to them (every imaginary part would be an exact zero).
+ * Same argument meaning as the _c128 entries above; there is no conjugation flag. */
+size_t mf_gemm_tn_f64_ws_bytes(int ra, int rb, int64_t n);
+int mf_gemm_tn_f64(const double* A, int64_t lda, int ra, const double* B, int64_t ldb, int rb, int64_t n,
+                   double* C, int64_t ldc, void* ws, size_t ws_bytes, void* stream);
+int mf_gemm_nn_f64(const double* A, int64_t lda, int64_t n, int ra, const double* W, int64_t ldw, int rb,
+                   double* Out, int64_t ldo, void* stream);
+int mf_spmm_csr_f64(const int32_t* rowptr, const int32_t* colidx, const double* vals, int64_t nrows,
+                    const double* Q, int64_t ldq, int r, double* Y, int64_t ldy, void* stream);
+int mf_spmm_grouped_f64(const int64_t* ustart, const int32_t* ucols, const double* uvals, int64_t nrows, int G,
+                        const double* Q, int64_t ldq, int r, double* Y, int64_t ldy, void* stream);
+int mf_project_rhs_f64(const int32_t* colptr, const int32_t* rowidx, const double* vals, int m,
+                       const double* Q, int64_t ldq, int r, int64_t row0, int64_t nlocal, double* Br, int64_t ldb, void* stream);
+
 /* As (r x r) = (A + A^T) / 2: the symmetrisation of implementation.py:528 hoisted out of the sweep loop
  * (linear in the operators, so applying it once to each reduced operator is the same mathematics). */
 int mf_symmetrize_c128(const mf_c128* A, int64_t lda, int r, mf_c128* As, int64_t lds, void* stream);

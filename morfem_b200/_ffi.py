@@ -43,6 +43,13 @@ SIGNATURES = {
                                      c_void_p]),
     "mf_project_rhs_c128": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int64, c_int, c_int64, c_int64,
                                     c_int, c_void_p, c_int64, c_void_p]),
+    "mf_gemm_tn_f64_ws_bytes": (c_size_t, [c_int, c_int, c_int64]),
+    "mf_gemm_tn_f64": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int64, c_int, c_int64, c_void_p, c_int64, c_void_p, c_size_t, c_void_p]),
+    "mf_gemm_nn_f64": (c_int, [c_void_p, c_int64, c_int64, c_int, c_void_p, c_int64, c_int, c_void_p, c_int64, c_void_p]),
+    "mf_spmm_csr_f64": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int, c_void_p, c_int64, c_void_p]),
+    "mf_spmm_grouped_f64": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_int64, c_int, c_void_p, c_int64, c_void_p]),
+    "mf_project_rhs_f64": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int64, c_int, c_int64, c_int64, c_void_p, c_int64,
+                                   c_void_p]),
     "mf_symmetrize_c128": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int64, c_void_p]),
     "mf_sweep_ws_bytes": (c_size_t, [c_int, c_int, c_int64, c_int]),
     "mf_sweep_variant_supported": (c_int, [c_int, c_int, c_int]),

@@ -212,6 +212,115 @@ __global__ void project_rhs_kernel(const int* __restrict__ colptr, const int* __
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// Real float64 twins (real operator values, real Q): same access pattern, 8-byte elements.
+template <int CPL>
+__global__ void __launch_bounds__(256)
+spmm_csr_f64_kernel(const int* __restrict__ rowptr, const int* __restrict__ colidx, const double* __restrict__ vals,
+                    long long nrows, const double* __restrict__ Q, long long ldq, int r, double* __restrict__ Y, long long ldy) {
+    const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (row >= nrows) return;
+    const int s = rowptr[row], e = rowptr[row + 1];
+    double acc[CPL];
+#pragma unroll
+    for (int c = 0; c < CPL; ++c) acc[c] = 0.0;
+    for (int base = s; base < e; base += 32) {
+        const int cnt = min(32, e - base);
+        int my_col = 0; double my_val = 0.0;
+        if (lane < cnt) { my_col = colidx[base + lane]; my_val = vals[base + lane]; }
+#pragma unroll 4
+        for (int k = 0; k < cnt; ++k) {
+            const int col = __shfl_sync(0xffffffffu, my_col, k);
+            const double v = __shfl_sync(0xffffffffu, my_val, k);
+            const double* q = Q + (long long)col * ldq;
+#pragma unroll
+            for (int c = 0; c < CPL; ++c) { const int idx = lane + 32 * c; if (idx < r) acc[c] = fma(v, __ldg(q + idx), acc[c]); }
+        }
+    }
+    double* y = Y + row * ldy;
+#pragma unroll
+    for (int c = 0; c < CPL; ++c) { const int idx = lane + 32 * c; if (idx < r) y[idx] = acc[c]; }
+}
+
+template <int G, int CPL>
+__global__ void __launch_bounds__(256)
+spmm_grouped_f64_kernel(const long long* __restrict__ ustart, const int* __restrict__ ucols, const double* __restrict__ uvals, long long nrows,
+                        const double* __restrict__ Q, long long ldq, int r, double* __restrict__ Y, long long ldy) {
+    const long long g = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    __shared__ __align__(16) double cstage[8][32 * G];
+    double* cw = cstage[(threadIdx.x >> 5) & 7];
+    if (g * G >= nrows) return;
+    const long long s = ustart[g], e = ustart[g + 1];
+    double acc[G][CPL];
+#pragma unroll
+    for (int i = 0; i < G; ++i)
+#pragma unroll
+        for (int c = 0; c < CPL; ++c) acc[i][c] = 0.0;
+    for (long long base = s; base < e; base += 32) {
+        const int cnt = (int)min((long long)32, e - base);
+        int my_col = 0;
+        if (lane < cnt) {
+            my_col = ucols[base + lane];
+            const double2* src = reinterpret_cast<const double2*>(uvals + (base + lane) * G);
+            double2* dst = reinterpret_cast<double2*>(cw + lane * G);
+            dst[0] = src[0];
+            if (G == 4) dst[1] = src[1];
+        }
+        __syncwarp();
+#pragma unroll 4
+        for (int k = 0; k < cnt; ++k) {
+            const int col = __shfl_sync(0xffffffffu, my_col, k);
+            const double* q = Q + (long long)col * ldq;
+            double qv[CPL];
+#pragma unroll
+            for (int c = 0; c < CPL; ++c) { const int idx = lane + 32 * c; qv[c] = idx < r ? __ldg(q + idx) : 0.0; }
+            double v[G];
+            {
+                const double2* vp = reinterpret_cast<const double2*>(cw + k * G);
+                const double2 t0 = vp[0];
+                v[0] = t0.x; v[1] = t0.y;
+                if (G == 4) { const double2 t1 = vp[1]; v[G > 2 ? 2 : 0] = t1.x; v[G > 3 ? 3 : 0] = t1.y; }
+            }
+#pragma unroll
+            for (int i = 0; i < G; ++i) {
+                if (v[i] != 0.0) {
+#pragma unroll
+                    for (int c = 0; c < CPL; ++c) acc[i][c] = fma(v[i], qv[c], acc[i][c]);
+                }
+            }
+        }
+        __syncwarp();
+    }
+#pragma unroll
+    for (int i = 0; i < G; ++i) {
+        const long long row = g * G + i;
+        if (row < nrows) {
+            double* y = Y + row * ldy;
+#pragma unroll
+            for (int c = 0; c < CPL; ++c) { const int idx = lane + 32 * c; if (idx < r) y[idx] = acc[i][c]; }
+        }
+    }
+}
+
+__global__ void project_rhs_f64_kernel(const int* __restrict__ colptr, const int* __restrict__ rowidx, const double* __restrict__ vals,
+                                       const double* __restrict__ Q, long long ldq, int r, long long row0, long long nlocal,
+                                       double* __restrict__ Br, long long ldb) {
+    const int col = blockIdx.x;
+    const int s = colptr[col], e = colptr[col + 1];
+    for (int i = threadIdx.x; i < r; i += blockDim.x) {
+        double acc = 0.0;
+        for (int p = s; p < e; ++p) {
+            const long long row = rowidx[p];
+            if (row < row0 || row >= row0 + nlocal) continue;
+            acc = fma(Q[(row - row0) * ldq + i], vals[p], acc);
+        }
+        Br[i * ldb + col] = acc;
+    }
+}
+
 }  // namespace
 
 extern "C" int mf_spmm_csr_c128(const int32_t* rowptr, const int32_t* colidx, const void* vals, int val_is_real,
@@ -307,6 +416,62 @@ extern "C" int mf_spmm_grouped_c128(const int64_t* ustart, const int32_t* ucols,
     else if (r <= 256) GSPMM(2, 8);
     else GSPMM(2, 16);
 #undef GSPMM
+    MF_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int mf_spmm_csr_f64(const int32_t* rowptr, const int32_t* colidx, const double* vals, int64_t nrows,
+                               const double* Q, int64_t ldq, int r, double* Y, int64_t ldy, void* stream) {
+    if (!rowptr) MF_FAIL_ARG(1, "rowptr is NULL");
+    if (!colidx) MF_FAIL_ARG(2, "colidx is NULL");
+    if (!vals) MF_FAIL_ARG(3, "vals is NULL");
+    if (nrows < 0) MF_FAIL_ARG(4, "nrows < 0");
+    if (!Q || ldq < r) MF_FAIL_ARG(5, "Q is NULL or ldq < r");
+    if (r <= 0 || r > 512) MF_FAIL_ARG(7, "need 0 < r <= 512");
+    if (!Y || ldy < r) MF_FAIL_ARG(8, "Y is NULL or ldy < r");
+    if (nrows == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long blocks = (nrows * 32 + 255) / 256;
+    if (blocks > 0x7fffffffLL) MF_FAIL_ARG(4, "nrows too large for one launch");
+#define RSPMM(C) spmm_csr_f64_kernel<C><<<(unsigned)blocks, 256, 0, st>>>(rowptr, colidx, vals, nrows, Q, ldq, r, Y, ldy)
+    if (r <= 32) RSPMM(1); else if (r <= 64) RSPMM(2); else if (r <= 128) RSPMM(4); else if (r <= 256) RSPMM(8); else RSPMM(16);
+#undef RSPMM
+    MF_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int mf_spmm_grouped_f64(const int64_t* ustart, const int32_t* ucols, const double* uvals, int64_t nrows, int G,
+                                   const double* Q, int64_t ldq, int r, double* Y, int64_t ldy, void* stream) {
+    if (!ustart) MF_FAIL_ARG(1, "ustart is NULL");
+    if (!ucols) MF_FAIL_ARG(2, "ucols is NULL");
+    if (!uvals) MF_FAIL_ARG(3, "uvals is NULL");
+    if (nrows < 0) MF_FAIL_ARG(4, "nrows < 0");
+    if (r <= 0 || r > 512) MF_FAIL_ARG(8, "need 0 < r <= 512");
+    if (G != mf_spmm_group_size(r)) MF_FAIL_ARG(5, "group size must equal mf_spmm_group_size(r)");
+    if (!Q || ldq < r) MF_FAIL_ARG(6, "Q is NULL or ldq < r");
+    if (!Y || ldy < r) MF_FAIL_ARG(9, "Y is NULL or ldy < r");
+    if (nrows == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long ngroups = (nrows + G - 1) / G;
+    const long long blocks = (ngroups * 32 + 255) / 256;
+    if (blocks > 0x7fffffffLL) MF_FAIL_ARG(4, "nrows too large for one launch");
+#define GRSPMM(GG, C) spmm_grouped_f64_kernel<GG, C><<<(unsigned)blocks, 256, 0, st>>>((const long long*)ustart, ucols, uvals, nrows, Q, ldq, r, Y, ldy)
+    if (r <= 32) GRSPMM(4, 1); else if (r <= 64) GRSPMM(4, 2); else if (r <= 128) GRSPMM(4, 4); else if (r <= 256) GRSPMM(2, 8); else GRSPMM(2, 16);
+#undef GRSPMM
+    MF_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int mf_project_rhs_f64(const int32_t* colptr, const int32_t* rowidx, const double* vals, int m,
+                                  const double* Q, int64_t ldq, int r, int64_t row0, int64_t nlocal, double* Br, int64_t ldb, void* stream) {
+    if (!colptr) MF_FAIL_ARG(1, "colptr is NULL");
+    if (!rowidx) MF_FAIL_ARG(2, "rowidx is NULL");
+    if (!vals) MF_FAIL_ARG(3, "vals is NULL");
+    if (m <= 0) MF_FAIL_ARG(4, "m <= 0");
+    if (!Q || ldq < r) MF_FAIL_ARG(5, "Q is NULL or ldq < r");
+    if (r <= 0) MF_FAIL_ARG(7, "r <= 0");
+    if (!Br || ldb < m) MF_FAIL_ARG(10, "Br is NULL or ldb < m");
+    project_rhs_f64_kernel<<<m, 256, 0, (cudaStream_t)stream>>>(colptr, rowidx, vals, Q, ldq, r, row0, nlocal, Br, ldb);
     MF_CHECK_LAUNCH();
     return 0;
 }

@@ -39,9 +39,19 @@ def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+F64 = torch.float64
+
+
 def _check_mat(t: torch.Tensor, name: str):
-    if t.dtype != C128 or not t.is_cuda or t.dim() != 2 or t.stride(1) != 1:
-        raise ValueError(f"{name}: expected a row-major complex128 CUDA matrix, got {t.dtype} {tuple(t.shape)} strides {t.stride()}")
+    if t.dtype not in (C128, F64) or not t.is_cuda or t.dim() != 2 or t.stride(1) != 1:
+        raise ValueError(f"{name}: expected a row-major complex128 or float64 CUDA matrix, got {t.dtype} {tuple(t.shape)} strides {t.stride()}")
+
+
+def _same_dtype(a: torch.Tensor, b: torch.Tensor, what: str) -> bool:
+    """True when both operands are real float64 (the real twins run), False when both are complex128."""
+    if a.dtype != b.dtype:
+        raise ValueError(f"{what}: operands must share a dtype (float64 or complex128), got {a.dtype} and {b.dtype}")
+    return a.dtype == F64
 
 
 def to_device_c128(a, device=None) -> torch.Tensor:
@@ -51,17 +61,21 @@ def to_device_c128(a, device=None) -> torch.Tensor:
     return upload(arr, device)
 
 
-def real_or_complex_to_device(a, device=None) -> torch.Tensor:
-    """Host ndarray -> complex128 device tensor, copying only the bytes the host array has: a real float64 array
-    is uploaded as float64 (half the PCIe traffic) and widened on the device."""
+def real_or_complex_to_device(a, device=None, widen: bool = False) -> torch.Tensor:
+    """Host ndarray -> device tensor in its own field: complex input -> complex128, real input -> float64 (half the
+    PCIe traffic and, with ``widen=False``, the real float64 twins of the stage-1/2 kernels).  ``widen=True`` converts
+    real data to complex128 on the device (the complex128 kernels of the north star run on real data too)."""
     device = device or require_cuda()
     if isinstance(a, torch.Tensor):
         t = a.to(device, non_blocking=True)
-        return t if t.dtype == C128 else t.to(C128)
+        if t.dtype == C128 or (t.dtype == F64 and not widen):
+            return t
+        return t.to(C128) if (widen or t.is_complex()) else t.to(F64)
     arr = np.asarray(a)
     if np.iscomplexobj(arr):
         return to_device_c128(arr, device)
-    return upload(np.ascontiguousarray(arr, dtype=np.float64), device).to(C128)
+    t = upload(np.ascontiguousarray(arr, dtype=np.float64), device)
+    return t.to(C128) if widen else t
 
 
 class _Workspaces:
@@ -128,18 +142,26 @@ class _timed:
 
 # ------------------------------------------------------------------------------------------ dense wrappers
 def gemm_tn(a: torch.Tensor, b: torch.Tensor, conj: bool = False, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """``op(a)^T b`` (ra x rb), reduction over the rows; ``conj`` selects ``a^H``."""
+    """``op(a)^T b`` (ra x rb), reduction over the rows; ``conj`` selects ``a^H``.  float64 operands run the real twin."""
     lib = _ffi.load()
     _check_mat(a, "a"); _check_mat(b, "b")
+    real = _same_dtype(a, b, "gemm_tn")
     n, ra = a.shape
     rb = b.shape[1]
     if b.shape[0] != n:
         raise ValueError("gemm_tn: row counts differ")
     if out is None:
-        out = torch.empty((ra, rb), dtype=C128, device=a.device)
+        out = torch.empty((ra, rb), dtype=a.dtype, device=a.device)
+    same = a.data_ptr() == b.data_ptr() and ra == rb
+    if real:
+        nbytes = lib.mf_gemm_tn_f64_ws_bytes(ra, rb, n)
+        ws = workspaces.get("gemm_tn", nbytes, a.device)
+        with _timed("gemm_tn", nbytes=8.0 * n * (ra if same else ra + rb) + 8.0 * ra * rb, flops=2.0 * n * ra * rb):
+            _ffi.check(lib.mf_gemm_tn_f64(_ptr(a), a.stride(0), ra, _ptr(b), b.stride(0), rb, n, _ptr(out), out.stride(0),
+                                          _ptr(ws), ws.numel(), _stream()), "mf_gemm_tn_f64")
+        return out
     nbytes = lib.mf_gemm_tn_ws_bytes(ra, rb, n)
     ws = workspaces.get("gemm_tn", nbytes, a.device)
-    same = a.data_ptr() == b.data_ptr() and ra == rb
     with _timed("gemm_tn", nbytes=16.0 * n * (ra if same else ra + rb) + 16.0 * ra * rb, flops=8.0 * n * ra * rb):
         _ffi.check(lib.mf_gemm_tn_c128(_ptr(a), a.stride(0), ra, _ptr(b), b.stride(0), rb, n, int(conj), _ptr(out), out.stride(0),
                                        _ptr(ws), ws.numel(), _stream()), "mf_gemm_tn_c128")
@@ -147,15 +169,21 @@ def gemm_tn(a: torch.Tensor, b: torch.Tensor, conj: bool = False, out: Optional[
 
 
 def gemm_nn(a: torch.Tensor, w: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """``a @ w`` for a tall ``a`` (n x ra) and a small ``w`` (ra x rb)."""
+    """``a @ w`` for a tall ``a`` (n x ra) and a small ``w`` (ra x rb).  float64 operands run the real twin."""
     lib = _ffi.load()
     _check_mat(a, "a"); _check_mat(w, "w")
+    real = _same_dtype(a, w, "gemm_nn")
     n, ra = a.shape
     if w.shape[0] != ra:
         raise ValueError("gemm_nn: inner dimensions differ")
     rb = w.shape[1]
     if out is None:
-        out = torch.empty((n, rb), dtype=C128, device=a.device)
+        out = torch.empty((n, rb), dtype=a.dtype, device=a.device)
+    if real:
+        with _timed("gemm_nn", nbytes=8.0 * n * (ra + rb) + 8.0 * ra * rb, flops=2.0 * n * ra * rb):
+            _ffi.check(lib.mf_gemm_nn_f64(_ptr(a), a.stride(0), n, ra, _ptr(w), w.stride(0), rb, _ptr(out), out.stride(0), _stream()),
+                       "mf_gemm_nn_f64")
+        return out
     with _timed("gemm_nn", nbytes=16.0 * n * (ra + rb) + 16.0 * ra * rb, flops=8.0 * n * ra * rb):
         _ffi.check(lib.mf_gemm_nn_c128(_ptr(a), a.stride(0), n, ra, _ptr(w), w.stride(0), rb, _ptr(out), out.stride(0), _stream()),
                    "mf_gemm_nn_c128")
@@ -272,16 +300,31 @@ def spmm(a: DeviceCSR, q: torch.Tensor, out: Optional[torch.Tensor] = None, col_
     lib = _ffi.load()
     _check_mat(q, "q")
     r = q.shape[1]
+    real = q.dtype == F64
+    if real and not a.is_real:
+        raise ValueError("spmm: a real float64 Q needs a real operator (convert Q to complex128 for complex operators)")
     if out is None:
-        out = torch.empty((a.nrows, r), dtype=C128, device=q.device)
+        out = torch.empty((a.nrows, r), dtype=q.dtype, device=q.device)
+    w = 8.0 if real else 16.0
     if a.grouped is not None and col_offset == 0 and a.grouped[0] == int(lib.mf_spmm_group_size(r)):
         g, ustart, ucols, uvals = a.grouped
+        if real:
+            nbytes = ucols.numel() * (4.0 + 8.0 * g) + 8.0 * ustart.numel() + w * r * (a.nrows + q.shape[0])
+            with _timed("spmm_csr", nbytes=nbytes, flops=2.0 * a.nnz * r):
+                _ffi.check(lib.mf_spmm_grouped_f64(_ptr(ustart), _ptr(ucols), _ptr(uvals), a.nrows, g, _ptr(q), q.stride(0), r,
+                                                   _ptr(out), out.stride(0), _stream()), "mf_spmm_grouped_f64")
+            return out
         nbytes = ucols.numel() * (4.0 + 8.0 * g) + 8.0 * ustart.numel() + 16.0 * r * (a.nrows + q.shape[0])
         with _timed("spmm_csr", nbytes=nbytes, flops=4.0 * a.nnz * r):
             _ffi.check(lib.mf_spmm_grouped_c128(_ptr(ustart), _ptr(ucols), _ptr(uvals), a.nrows, g, _ptr(q), q.stride(0), r,
                                                 _ptr(out), out.stride(0), _stream()), "mf_spmm_grouped_c128")
         return out
     colidx = a.colidx if col_offset == 0 else a.colidx - col_offset
+    if real:
+        with _timed("spmm_csr", nbytes=a.nnz * 12.0 + 4.0 * (a.nrows + 1) + w * r * (a.nrows + q.shape[0]), flops=2.0 * a.nnz * r):
+            _ffi.check(lib.mf_spmm_csr_f64(_ptr(a.rowptr), _ptr(colidx), _ptr(a.vals), a.nrows, _ptr(q), q.stride(0), r,
+                                           _ptr(out), out.stride(0), _stream()), "mf_spmm_csr_f64")
+        return out
     valb = 8.0 if a.is_real else 16.0
     with _timed("spmm_csr", nbytes=a.nnz * (valb + 4.0) + 4.0 * (a.nrows + 1) + 16.0 * r * (a.nrows + q.shape[0]),
                 flops=(4.0 if a.is_real else 8.0) * a.nnz * r):
@@ -319,6 +362,13 @@ def project_rhs(b: DeviceCSC, q: torch.Tensor, row0: int = 0, conj: bool = False
     lib = _ffi.load()
     _check_mat(q, "q")
     r = q.shape[1]
+    if q.dtype == F64:
+        if not b.is_real:
+            raise ValueError("project_rhs: a real float64 Q needs a real port matrix")
+        out = torch.empty((r, b.ncols), dtype=F64, device=q.device)
+        _ffi.check(lib.mf_project_rhs_f64(_ptr(b.colptr), _ptr(b.rowidx), _ptr(b.vals), b.ncols, _ptr(q), q.stride(0), r,
+                                          row0, q.shape[0], _ptr(out), out.stride(0), _stream()), "mf_project_rhs_f64")
+        return out
     out = torch.empty((r, b.ncols), dtype=C128, device=q.device)
     _ffi.check(lib.mf_project_rhs_c128(_ptr(b.colptr), _ptr(b.rowidx), _ptr(b.vals), int(b.is_real), b.ncols, _ptr(q), q.stride(0), r,
                                        row0, q.shape[0], int(conj), _ptr(out), out.stride(0), _stream()), "mf_project_rhs_c128")
@@ -330,7 +380,17 @@ def _allreduce(t: torch.Tensor, group) -> None:
     if group is None:
         return
     import torch.distributed as dist
-    dist.all_reduce(torch.view_as_real(t), op=dist.ReduceOp.SUM, group=group)
+    dist.all_reduce(torch.view_as_real(t) if t.is_complex() else t, op=dist.ReduceOp.SUM, group=group)
+
+
+def _small_c128(t: torch.Tensor) -> torch.Tensor:
+    """r x r matrices of the real path go through the complex128 factorisation kernels (tiny, off the roofline)."""
+    return t if t.dtype == C128 else t.to(C128)
+
+
+def _like_block(small: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
+    """The small factor in the field of the tall block it multiplies (its imaginary part is exactly zero for real x)."""
+    return small if x.dtype == C128 else small.real.contiguous()
 
 
 class BasisInfo:
@@ -394,6 +454,7 @@ def _cholesky_qr2_optimistic(s: torch.Tensor, group=None) -> CholQR:
     for p in range(2):
         g = gemm_tn(x, x, conj=True)
         _allreduce(g, group)
+        g = _small_c128(g)
         stats = flags[p, :16].view(torch.float64)
         info = flags[p, 16:20].view(torch.int32)
         _ffi.check(lib.mf_equilibrate_c128(_ptr(g), g.stride(0), r, 0.0, _ptr(d), _ptr(stats), _stream()), "mf_equilibrate_c128")
@@ -403,7 +464,7 @@ def _cholesky_qr2_optimistic(s: torch.Tensor, group=None) -> CholQR:
         _ffi.check(lib.mf_trtri_upper_c128(_ptr(g), g.stride(0), r, _ptr(rinv), rinv.stride(0), _stream()), "mf_trtri_upper_c128")
         r_tot = g if r_tot is None else gemm_nn(g, r_tot)
         if p == 0:
-            x = gemm_nn(x, rinv)
+            x = gemm_nn(x, _like_block(rinv, x))
     return CholQR(x, r_tot, rinv, 2, [0.0, 0.0], flags)
 
 
@@ -430,6 +491,7 @@ def cholesky_qr(s: torch.Tensor, group=None, max_passes: int = 6, optimistic: bo
     for p in range(max_passes):
         g = gemm_tn(x, x, conj=True)
         _allreduce(g, group)
+        g = _small_c128(g)
         shift = 0.0
         while True:
             gw = g.clone()
@@ -454,8 +516,8 @@ def cholesky_qr(s: torch.Tensor, group=None, max_passes: int = 6, optimistic: bo
             return CholQR(x, r_tot, rinv, p + 1, shifts)
         tgt = p % 2
         if bufs[tgt] is None:
-            bufs[tgt] = torch.empty((n_loc, r), dtype=C128, device=dev)
-        x = gemm_nn(x, rinv, out=bufs[tgt])
+            bufs[tgt] = torch.empty((n_loc, r), dtype=s.dtype, device=dev)
+        x = gemm_nn(x, _like_block(rinv, x), out=bufs[tgt])
     raise AssertionError("unreachable")
 
 
@@ -498,7 +560,7 @@ def orthonormalize(s: torch.Tensor, truncation_tol: float = 0.0, group=None, n_g
     """
     cq = cholesky_qr(s, group=group, max_passes=max_passes)
     w, info = basis_rotation(cq, truncation_tol)
-    q = gemm_nn(cq.x, w)
+    q = gemm_nn(cq.x, _like_block(w, cq.x))
     return q, info
 
 
@@ -526,6 +588,7 @@ def basis_and_projection(s: torch.Tensor, project_block, group=None, truncation_
     side.wait_event(ev0)
     with torch.cuda.stream(side):
         w, info = basis_rotation(cq, truncation_tol)
+        w = _like_block(w, cq.x)
         q = gemm_nn(cq.x, w)
         ev1 = torch.cuda.Event()
         ev1.record(side)
@@ -534,8 +597,9 @@ def basis_and_projection(s: torch.Tensor, project_block, group=None, truncation_
         for t in (w, q, info._sigma, info._sweeps):
             if isinstance(t, torch.Tensor):
                 t.record_stream(main)
-    reduced = [None if g is None else gemm_nn(gemm_tn(w, g, conj=False), w) for g in g_list]
-    b_r = gemm_tn(w, bt, conj=False)
+    # (for a real block the reduced model is formed in float64 and handed to the complex128 sweep as complex128)
+    reduced = [None if g is None else _small_c128(gemm_nn(gemm_tn(w, g, conj=False), w)) for g in g_list]
+    b_r = _small_c128(gemm_tn(w, bt, conj=False))
     info.flags = cq.flags            # None unless optimistic: the caller verifies with flags_ok(flags.cpu())
     return q, reduced, b_r, info
 

@@ -296,8 +296,9 @@ def morfem_from_snapshots(snapshots: np.ndarray, domain: np.ndarray, a0: csc_arr
     from . import device as dv
     md = ModelDefinition(domain, a0, a1, a2, b, t_a0, t_a1, t_a2, t_b)
     ops = _DeviceOperators(md)
-    qd, (a0_r, a1_r, a2_r), b_r, _ = dv.basis_and_projection(dv.real_or_complex_to_device(snapshots), ops.project_block,
-                                                             truncation_tol=TRUNCATION_TOL)
+    all_real = _real_inputs(a0, a1, a2, b) and not np.iscomplexobj(snapshots)      # real data: float64 stage-1/2 kernels
+    qd, (a0_r, a1_r, a2_r), b_r, _ = dv.basis_and_projection(dv.real_or_complex_to_device(snapshots, widen=not all_real),
+                                                             ops.project_block, truncation_tol=TRUNCATION_TOL)
     res = _sweep_device(domain, [a0_r, a1_r, a2_r], b_r, t_a0, t_a1, t_a2, t_b, want_x=True, want_gsm=False)
     _warn_singular(res.info.cpu().numpy())
     real = _real_inputs(a0, a1, a2, b) and not np.iscomplexobj(snapshots)

@@ -109,18 +109,23 @@ def finite_element_method_model_order_reduction_gsm(frequency_points, gate_count
     return gsm
 
 
-def model_order_reduction_gsm_from_snapshots(frequency_points, snapshots, in_c, in_gamma, in_b, pinned_out=None):
+def model_order_reduction_gsm_from_snapshots(frequency_points, snapshots, in_c, in_gamma, in_b, pinned_out=None, real_path=None):
     """Stages 1-4 on a given snapshot block: the body of ``finite_element_method_model_order_reduction_gsm``
     (test_helpers.py:53-67) with the basis taken from ``svd(snapshots)[0]`` instead of the greedy search, so that no
     full-order SuperLU solve sits inside the call.  Host arrays in, (F, M, M) complex ndarray out; this is the call
-    bench.py times end to end."""
+    bench.py times end to end.  ``real_path``: None = automatic (real float64 stage-1/2 kernels when snapshots and
+    operators are all real, like the reference's data), False = always the complex128 kernels, True = require the real ones."""
     from . import device as dv
     import torch
     frequency_points = np.asarray(frequency_points, dtype=np.float64)
     md = ModelDefinition(frequency_points, in_c, csc_array(in_c.shape), in_gamma, in_b, lambda t: 1., lambda t: t, lambda t: t ** 2,
                          lambda t: b_coefficient(t))
     ops = impl._DeviceOperators(md)
-    _, (a0_r, a1_r, a2_r), b_r, _ = dv.basis_and_projection(dv.real_or_complex_to_device(snapshots), ops.project_block,
+    all_real = impl._real_inputs(in_c, in_gamma, in_b) and not np.iscomplexobj(snapshots)
+    if real_path and not all_real:
+        raise ValueError("real_path=True needs real snapshots and operators")
+    widen = not all_real if real_path is None else not real_path
+    _, (a0_r, a1_r, a2_r), b_r, _ = dv.basis_and_projection(dv.real_or_complex_to_device(snapshots, widen=widen), ops.project_block,
                                                             truncation_tol=impl.TRUNCATION_TOL)
     res = impl._sweep_device(frequency_points, [a0_r, a1_r, a2_r], b_r, md.t_a0, md.t_a1, md.t_a2, md.t_b, want_x=False, want_gsm=True)
     gsm = dv.download(res.gsm, pinned_out)

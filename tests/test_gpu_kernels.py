@@ -188,3 +188,42 @@ def test_spmm_row_grouped_matches_csr_kernel(dv, r):
         ref = (q.T @ a).T                                   # implementation.py:181: q_t @ a
         assert rel(y_grp, ref) < 1e-14
         assert rel(y_grp, y_csr) < 1e-14
+
+
+# ----------------------------------------------------------------------------------- real float64 twins (row N2)
+@pytest.mark.parametrize("n,ra,rb", [(1, 1, 1), (100, 3, 5), (4097, 64, 64), (30000, 33, 64), (9000, 130, 130), (2000, 256, 7)])
+def test_real_gemm_twins_match_numpy_and_the_complex_kernels(dv, n, ra, rb):
+    rng = np.random.default_rng(n + ra)
+    a, b = rng.standard_normal((n, ra)), rng.standard_normal((n, rb))
+    w = rng.standard_normal((ra, rb))
+    up = lambda x: torch.from_numpy(np.ascontiguousarray(x)).cuda()
+    c = dv.gemm_tn(up(a), up(b)).cpu().numpy()
+    assert c.dtype == np.float64 and rel(c, a.T @ b) < 1e-14
+    cc = dv.gemm_tn(dv.to_device_c128(a), dv.to_device_c128(b)).cpu().numpy()
+    assert rel(c, cc.real) < 1e-14 and np.abs(cc.imag).max() == 0.0
+    o = dv.gemm_nn(up(a), up(w)).cpu().numpy()
+    assert o.dtype == np.float64 and rel(o, a @ w) < 1e-14
+    # strided operands (column blocks of a wider matrix, odd leading dimension: the 8-byte copy path)
+    wide = rng.standard_normal((n, ra + rb + 1))
+    wd = up(wide)
+    cs = dv.gemm_tn(wd[:, :ra], wd[:, ra:ra + rb]).cpu().numpy()
+    assert rel(cs, wide[:, :ra].T @ wide[:, ra:ra + rb]) < 1e-14
+
+
+@pytest.mark.parametrize("r", [7, 64, 100, 200])
+def test_real_spmm_and_rhs_projection_twins(dv, r):
+    from morfem_b200 import synthetic
+    ct, _ = synthetic.waveguide_operators(6, 5, 41)
+    n = ct.shape[0]
+    rng = np.random.default_rng(r)
+    q = rng.standard_normal((n, r))
+    qd = torch.from_numpy(q).cuda()
+    csr = dv.csr_of_transpose(ct)
+    y_csr = dv.spmm(csr, qd).cpu().numpy()
+    dv.group_rows(csr, r)
+    y_grp = dv.spmm(csr, qd).cpu().numpy()
+    ref = (q.T @ ct).T
+    assert y_csr.dtype == np.float64 and rel(y_csr, ref) < 1e-14 and rel(y_grp, ref) < 1e-14
+    wp = synthetic.port_matrix(n, 3, 19)
+    br = dv.project_rhs(dv.csc_to_device(wp), qd).cpu().numpy()
+    assert br.dtype == np.float64 and rel(br, q.T @ wp) < 1e-14

@@ -270,3 +270,32 @@ def test_graph_replay_equals_eager_step_and_falls_back(dv):
     redo = path.verify()
     assert redo is not None
     assert orc.rel_err(redo[0].cpu().numpy(), path.step(bad, gather=False)[0].cpu().numpy()) < 1e-9
+
+
+def test_real_float64_stages_equal_the_complex_path(dv):
+    """Row N2: for real snapshots and operators the float64 twins of stages 1 + 2 give the complex128 path's reduced model
+    (same algorithm on 8-byte elements; every imaginary part of the complex run is an exact zero)."""
+    from morfem_b200 import implementation as impl, test_helpers as th
+    g = np.load(os.path.join(GOLDEN, "stages_n600.npz"))
+    in_c, in_gamma, in_b = operators_from(g)
+    keep = 10
+    md = impl.ModelDefinition(g["f"], in_c, csc_array(in_c.shape), in_gamma, in_b, lambda t: 1.0, lambda t: t, lambda t: t ** 2, th.b_coefficient)
+    ops = impl._DeviceOperators(md)
+    snaps = np.ascontiguousarray(g["snapshots"][:, :keep])
+    qc, rc, bc, _ = dv.basis_and_projection(dv.to_device_c128(snaps), ops.project_block)
+    qr, rr, br, info = dv.basis_and_projection(dv.real_or_complex_to_device(snaps), ops.project_block)
+    torch.cuda.synchronize()
+    assert qr.dtype == torch.float64 and rr[0].dtype == torch.complex128
+    assert orc.subspace_residual(qc.cpu().numpy().real, qr.cpu().numpy()) < 1e-9
+    # reduced operators live in each run's own basis; the S-parameters are basis invariant
+    f = g["f"]
+    sc = impl._sweep_device(f, list(rc), bc, md.t_a0, md.t_a1, md.t_a2, md.t_b, want_x=False, want_gsm=True).gsm.cpu().numpy()
+    sr = impl._sweep_device(f, list(rr), br, md.t_a0, md.t_a1, md.t_a2, md.t_b, want_x=False, want_gsm=True).gsm.cpu().numpy()
+    assert orc.rel_err(sr, sc) < 1e-8
+    ref = orc.galerkin_projection(qr.cpu().numpy(), in_c, md.a1, in_gamma, in_b)
+    for new, old in ((rr[0], ref[0]), (rr[2], ref[2]), (br, ref[3])):
+        assert orc.rel_err(new.cpu().numpy().real, old) < 1e-10
+    # end-to-end helper: automatic real path == forced complex path
+    s_auto = th.model_order_reduction_gsm_from_snapshots(f, snaps, in_c, in_gamma, in_b)
+    s_cplx = th.model_order_reduction_gsm_from_snapshots(f, snaps, in_c, in_gamma, in_b, real_path=False)
+    assert orc.rel_err(s_auto, s_cplx) < 1e-8
