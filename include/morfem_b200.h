@@ -114,6 +114,10 @@ int mf_spmm_csr_f64(const int32_t* rowptr, const int32_t* colidx, const double* 
                     const double* Q, int64_t ldq, int r, double* Y, int64_t ldy, void* stream);
 int mf_spmm_grouped_f64(const int64_t* ustart, const int32_t* ucols, const double* uvals, int64_t nrows, int G,
                         const double* Q, int64_t ldq, int r, double* Y, int64_t ldy, void* stream);
+/* One-sided Jacobi SVD of a REAL r x r matrix (r <= 64, see mf_jacobi_svd_f64_supported); X is not modified. */
+int mf_jacobi_svd_f64_supported(int r);
+int mf_jacobi_svd_f64(const double* X, int64_t ld, int r, double* U, int64_t ldu, double* sigma, int max_sweeps,
+                      double tol, int* sweeps_done, void* stream);
 int mf_project_rhs_f64(const int32_t* colptr, const int32_t* rowidx, const double* vals, int m,
                        const double* Q, int64_t ldq, int r, int64_t row0, int64_t nlocal, double* Br, int64_t ldb, void* stream);
 

@@ -365,6 +365,82 @@ jacobi_svd_smem_kernel(const cplx* __restrict__ Xin, long long ld, int r, cplx* 
     if (tid == 0 && sweeps_done) *sweeps_done = sweep;
 }
 
+
+// Real float64 twin of the single-CTA kernel (r <= 64): the triangular factor of a real snapshot block is real, and a
+// real plane rotation costs half the FP64 work of the complex one -- which is what bounds this kernel (one SM's FP64
+// pipe shared by 32 warps).
+__global__ void __launch_bounds__(1024)
+jacobi_svd_smem_f64_kernel(const double* __restrict__ Xin, long long ld, int r, double* __restrict__ U, long long ldu,
+                           double* __restrict__ sigma, int max_sweeps, double tol, int* sweeps_done) {
+    extern __shared__ __align__(16) double jsd_sm[];
+    __shared__ double sig[JS_SMEM_MAX];
+    __shared__ int rotated[2];
+    const int r2 = (r + 1) & ~1, ldx = r | 1, ldg = r2 | 1;
+    double* Xw = jsd_sm;                    // r2 x ldx
+    double* Gacc = Xw + (size_t)r2 * ldx;   // r2 x ldg
+    const int tid = threadIdx.x, lane = tid & 31, c = tid >> 5, nthreads = blockDim.x;
+    for (int idx = tid; idx < r2 * r; idx += nthreads) { int i = idx / r, k = idx - i * r; Xw[i * ldx + k] = i < r ? Xin[i * ld + k] : 0.0; }
+    for (int idx = tid; idx < r2 * r2; idx += nthreads) { int i = idx / r2, k = idx - i * r2; Gacc[i * ldg + k] = (i == k) ? 1.0 : 0.0; }
+    if (tid < 2) rotated[tid] = 0;
+    __syncthreads();
+    int sweep = 0;
+    for (; sweep < max_sweeps; ++sweep) {
+        for (int round = 0; round < r2 - 1; ++round) {
+            int p, q;
+            if (c == 0) { p = r2 - 1; q = round; }
+            else { p = (round + c) % (r2 - 1); q = (round - c + (r2 - 1)) % (r2 - 1); }
+            if (p > q) { int tmp = p; p = q; q = tmp; }
+            double* xp = Xw + p * ldx; double* xq = Xw + q * ldx;
+            double a = 0.0, b = 0.0, cr = 0.0;
+            for (int k = lane; k < r; k += 32) { const double u = xp[k], v = xq[k]; a = fma(u, u, a); b = fma(v, v, b); cr = fma(u, v, cr); }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                a += __shfl_xor_sync(0xffffffffu, a, off); b += __shfl_xor_sync(0xffffffffu, b, off); cr += __shfl_xor_sync(0xffffffffu, cr, off);
+            }
+            const double cabs = fabs(cr);
+            if (cabs > tol * sqrt(a * b) && cabs > 0.0) {
+                if (lane == 0) rotated[sweep & 1] = 1;
+                const double zeta = 0.5 * (b - a) / cabs;
+                const double tt = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(fma(zeta, zeta, 1.0)));
+                const double cs = rsqrt(fma(tt, tt, 1.0));
+                const double sn = (cr >= 0.0 ? cs * tt : -cs * tt);     // sn * sign(cr): the complex kernel's sn * e^{i phi}
+                for (int k = lane; k < r; k += 32) {
+                    const double u = xp[k], v = xq[k];
+                    xp[k] = fma(cs, u, -sn * v);
+                    xq[k] = fma(sn, u, cs * v);
+                }
+                double* gp = Gacc + p * ldg; double* gq = Gacc + q * ldg;
+                for (int k = lane; k < r2; k += 32) {
+                    const double u = gp[k], v = gq[k];
+                    gp[k] = fma(cs, u, -sn * v);
+                    gq[k] = fma(sn, u, cs * v);
+                }
+            }
+            __syncthreads();
+        }
+        const int any = rotated[sweep & 1];
+        if (tid == 0) rotated[(sweep + 1) & 1] = 0;
+        __syncthreads();
+        if (!any) { ++sweep; break; }
+    }
+    for (int row = c; row < r2; row += (nthreads >> 5)) {
+        double a = 0.0;
+        for (int k = lane; k < r; k += 32) { const double v = Xw[row * ldx + k]; a = fma(v, v, a); }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) a += __shfl_xor_sync(0xffffffffu, a, off);
+        if (lane == 0) sig[row] = sqrt(a);
+    }
+    __syncthreads();
+    for (int row = c; row < r; row += (nthreads >> 5)) {
+        const double sv = sig[row];
+        int rank = 0;
+        for (int j = 0; j < r; ++j) { const double sj = sig[j]; rank += (sj > sv) || (sj == sv && j < row); }
+        if (lane == 0) sigma[rank] = sv;
+        for (int k = lane; k < r; k += 32) U[k * ldu + rank] = Gacc[row * ldg + k];
+    }
+    if (tid == 0 && sweeps_done) *sweeps_done = sweep;
+}
+
 }  // namespace
 
 extern "C" int mf_equilibrate_c128(mf_c128* G, int64_t ld, int r, double shift, double* d, double* stats, void* stream) {
@@ -484,5 +560,23 @@ extern "C" int mf_jacobi_svd_c128(mf_c128* X, int64_t ld, int r, mf_c128* U, int
                     (void*)&sweeps_done, (void*)&Xw, (void*)&Gacc, (void*)&sig, (void*)&offmax, (void*)&counter};
     MF_CHECK_CUDA(cudaLaunchCooperativeKernel((const void*)jacobi_svd_kernel, dim3(grid), dim3(JS_THREADS), args, 0, st));
     g_mf_launches.fetch_add(1, std::memory_order_relaxed);
+    return 0;
+}
+
+/* 1 when mf_jacobi_svd_f64 supports this r (single-CTA shared-memory kernel), else 0 (use the complex128 entry). */
+extern "C" int mf_jacobi_svd_f64_supported(int r) { return (r >= 1 && r <= JS_SMEM_MAX) ? 1 : 0; }
+
+extern "C" int mf_jacobi_svd_f64(const double* X, int64_t ld, int r, double* U, int64_t ldu, double* sigma, int max_sweeps,
+                                 double tol, int* sweeps_done, void* stream) {
+    if (!X || ld < r) MF_FAIL_ARG(1, "X is NULL or ld < r");
+    if (r <= 0 || r > JS_SMEM_MAX) MF_FAIL_ARG(3, "need 0 < r <= 64 (mf_jacobi_svd_f64_supported)");
+    if (!U || ldu < r) MF_FAIL_ARG(4, "U is NULL or ldu < r");
+    if (!sigma) MF_FAIL_ARG(6, "sigma is NULL");
+    if (max_sweeps <= 0 || max_sweeps > 64) MF_FAIL_ARG(7, "need 0 < max_sweeps <= 64");
+    const size_t r2 = (size_t)((r + 1) & ~1);
+    const size_t smem = sizeof(double) * (r2 * (size_t)(r | 1) + r2 * (r2 | 1));
+    MF_CHECK_CUDA(cudaFuncSetAttribute(jacobi_svd_smem_f64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    jacobi_svd_smem_f64_kernel<<<1, (unsigned)(32 * (r2 / 2)), smem, (cudaStream_t)stream>>>(X, ld, r, U, ldu, sigma, max_sweeps, tol, sweeps_done);
+    MF_CHECK_LAUNCH();
     return 0;
 }

@@ -535,10 +535,19 @@ def basis_rotation(cq: CholQR, truncation_tol: float = 0.0) -> tuple[torch.Tenso
     sweeps = torch.zeros(1, dtype=torch.int32, device=dev)
     nbytes = lib.mf_jacobi_svd_ws_bytes(r)
     ws = workspaces.get("jacobi", nbytes, dev)
-    r_work = r_tot.clone()           # the SVD destroys its input; keep r_tot (S = x r_tot) for the caller
-    with _timed("jacobi_svd"):
-        _ffi.check(lib.mf_jacobi_svd_c128(_ptr(r_work), r_work.stride(0), r, _ptr(u), u.stride(0), _ptr(sigma), 40, 4.0 * eps,
-                                          _ptr(sweeps), _ptr(ws), ws.numel(), _stream()), "mf_jacobi_svd_c128")
+    if cq.x.dtype == F64 and lib.mf_jacobi_svd_f64_supported(r):
+        # real block: the triangular factor is real; the real rotation kernel does half the FP64 work
+        r_real = r_tot.real.contiguous()
+        u_real = torch.empty((r, r), dtype=F64, device=dev)
+        with _timed("jacobi_svd"):
+            _ffi.check(lib.mf_jacobi_svd_f64(_ptr(r_real), r_real.stride(0), r, _ptr(u_real), u_real.stride(0), _ptr(sigma), 40, 4.0 * eps,
+                                             _ptr(sweeps), _stream()), "mf_jacobi_svd_f64")
+        u = u_real.to(C128)
+    else:
+        r_work = r_tot.clone()           # the SVD destroys its input; keep r_tot (S = x r_tot) for the caller
+        with _timed("jacobi_svd"):
+            _ffi.check(lib.mf_jacobi_svd_c128(_ptr(r_work), r_work.stride(0), r, _ptr(u), u.stride(0), _ptr(sigma), 40, 4.0 * eps,
+                                              _ptr(sweeps), _ptr(ws), ws.numel(), _stream()), "mf_jacobi_svd_c128")
     keep = r
     if truncation_tol > 0.0:
         sig = sigma.cpu().numpy()

@@ -227,3 +227,28 @@ def test_real_spmm_and_rhs_projection_twins(dv, r):
     wp = synthetic.port_matrix(n, 3, 19)
     br = dv.project_rhs(dv.csc_to_device(wp), qd).cpu().numpy()
     assert br.dtype == np.float64 and rel(br, q.T @ wp) < 1e-14
+
+
+@pytest.mark.parametrize("r", [1, 2, 9, 32, 63, 64])
+def test_real_jacobi_svd_twin(dv, r):
+    import ctypes
+    from morfem_b200 import _ffi
+    lib = _ffi.load()
+    rng = np.random.default_rng(r)
+    m = np.triu(rng.standard_normal((r, r))) * (10.0 ** (-4.0 * np.arange(r) / max(r - 1, 1)))[None, :]
+    md = torch.from_numpy(np.ascontiguousarray(m)).cuda()
+    u = torch.empty((r, r), dtype=torch.float64, device="cuda")
+    sigma = torch.empty(r, dtype=torch.float64, device="cuda")
+    sweeps = torch.zeros(1, dtype=torch.int32, device="cuda")
+    P = lambda t: ctypes.c_void_p(t.data_ptr())
+    assert lib.mf_jacobi_svd_f64_supported(r) == 1
+    _ffi.check(lib.mf_jacobi_svd_f64(P(md), r, r, P(u), r, P(sigma), 40, 4 * np.finfo(float).eps, P(sweeps), None), "mf_jacobi_svd_f64")
+    torch.cuda.synchronize()
+    uh, sh = u.cpu().numpy(), sigma.cpu().numpy()
+    s_ref = np.linalg.svd(m, compute_uv=False)
+    assert np.all(np.diff(sh) <= 0) and np.max(np.abs(sh - s_ref)) < 1e-13 * s_ref[0]
+    assert rel(uh.T @ uh, np.eye(r)) < 1e-13
+    t = uh.T @ m                                            # rows orthogonal with norms sigma
+    gram = t @ t.T
+    assert np.max(np.abs(gram - np.diag(np.diag(gram)))) < 1e-12 * s_ref[0] ** 2
+    assert 0 < int(sweeps.item()) < 40
