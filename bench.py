@@ -358,7 +358,7 @@ def run_b200(args, wl, rank, world, local_rank):
         sweep_k = kernels.get("sweep_lu_gsm", {})
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "c128" if not real else "f64 (stages 1+2) / c128 (sweep)", "data": "synthetic",
+                "dtype": "c128" if not real else "f64", "data": "synthetic",
                 "config": {"workload": args.workload + ": " + wl["desc"], "N_dof_per_gpu": n // world, "N_dof_total": n, "r": wl["r"], "ports": wl["m"],
                            "freq_points_total": f_total, "step": "basis (CholeskyQR2+SVD) + projection + reduced solves + S-parameters" + (", replayed from one CUDA graph" if use_graph else ""),
                            "l2": "inputs larger than L2 (snapshot block %.0f MB + operators per GPU); no flush" % (s_dev.numel() * s_dev.element_size() / 1e6),
@@ -383,8 +383,8 @@ def main():
     ap.add_argument("--cpu-points", type=int, default=2000, help="sweep points the CPU arm solves per step (scaled to the full axis)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--dtype", default="c128", choices=["c128", "f64"],
-                    help="c128: complex128 kernels throughout (north star); f64: real float64 twins for stages 1+2 (the reference's dtype), "
-                         "complex128 sweep")
+                    help="c128: complex128 kernels throughout (north star); f64: the real float64 twins (the reference's own dtype; "
+                         "valid because the synthetic operators and snapshots are real, like the reference's data)")
     ap.add_argument("--no-graph", action="store_true", help="run the eager (adaptive CholeskyQR) step instead of the CUDA-graph replay at N=1")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]

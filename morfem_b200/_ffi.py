@@ -48,6 +48,9 @@ SIGNATURES = {
     "mf_gemm_nn_f64": (c_int, [c_void_p, c_int64, c_int64, c_int, c_void_p, c_int64, c_int, c_void_p, c_int64, c_void_p]),
     "mf_spmm_csr_f64": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int, c_void_p, c_int64, c_void_p]),
     "mf_spmm_grouped_f64": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_int64, c_int, c_void_p, c_int64, c_void_p]),
+    "mf_sweep_f64_supported": (c_int, [c_int, c_int]),
+    "mf_sweep_lu_gsm_f64": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int,
+                                    c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "mf_jacobi_svd_f64_supported": (c_int, [c_int]),
     "mf_jacobi_svd_f64": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int64, c_void_p, c_int, c_double, c_void_p, c_void_p]),
     "mf_project_rhs_f64": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int64, c_int, c_int64, c_int64, c_void_p, c_int64,

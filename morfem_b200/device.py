@@ -195,6 +195,8 @@ def symmetrize(a: torch.Tensor) -> torch.Tensor:
     lib = _ffi.load()
     _check_mat(a, "a")
     r = a.shape[0]
+    if a.dtype == F64:
+        return ((a + a.T) * 0.5).contiguous()      # r x r, literally implementation.py:528
     out = torch.empty((r, r), dtype=C128, device=a.device)
     _ffi.check(lib.mf_symmetrize_c128(_ptr(a), a.stride(0), r, _ptr(out), out.stride(0), _stream()), "mf_symmetrize_c128")
     return out
@@ -606,9 +608,9 @@ def basis_and_projection(s: torch.Tensor, project_block, group=None, truncation_
         for t in (w, q, info._sigma, info._sweeps):
             if isinstance(t, torch.Tensor):
                 t.record_stream(main)
-    # (for a real block the reduced model is formed in float64 and handed to the complex128 sweep as complex128)
-    reduced = [None if g is None else _small_c128(gemm_nn(gemm_tn(w, g, conj=False), w)) for g in g_list]
-    b_r = _small_c128(gemm_tn(w, bt, conj=False))
+    # (for a real block the reduced model stays float64: the sweep has a real twin)
+    reduced = [None if g is None else gemm_nn(gemm_tn(w, g, conj=False), w) for g in g_list]
+    b_r = gemm_tn(w, bt, conj=False)
     info.flags = cq.flags            # None unless optimistic: the caller verifies with flags_ok(flags.cpu())
     return q, reduced, b_r, info
 
@@ -638,6 +640,14 @@ def sweep(a0s: Optional[torch.Tensor], a1s: Optional[torch.Tensor], a2s: Optiona
         _check_mat(o, "operator")
     _check_mat(br, "br")
     r, m = br.shape
+    if all(o.dtype == F64 for o in ops) and br.dtype == F64:
+        if variant in (0, 3) and lib.mf_sweep_f64_supported(r, m):
+            return _sweep_f64(lib, a0s, a1s, a2s, br, c0, c1, c2, cb, zscale, want_x, want_gsm)
+        a0s, a1s, a2s = (None if o is None else o.to(C128) for o in (a0s, a1s, a2s))     # no real kernel for this shape
+        br = br.to(C128)
+        ops = [o for o in (a0s, a1s, a2s) if o is not None]
+    elif any(o.dtype != C128 for o in ops) or br.dtype != C128:
+        raise ValueError("sweep: operators and port matrix must share a dtype (all float64 or all complex128)")
     lda = ops[0].stride(0)
     if any(o.stride(0) != lda or o.shape != (r, r) for o in ops):
         raise ValueError("sweep: operators must share shape (r, r) and leading dimension")
@@ -659,6 +669,27 @@ def sweep(a0s: Optional[torch.Tensor], a1s: Optional[torch.Tensor], a2s: Optiona
                                             _ptr(x), _ptr(gsm), _ptr(info), variant, _ptr(ws), ws.numel(), _stream()),
                    "mf_sweep_lu_gsm_c128")
     return SweepResult(x, gsm, info)
+
+
+def _sweep_f64(lib, a0s, a1s, a2s, br, c0, c1, c2, cb, zscale, want_x, want_gsm) -> SweepResult:
+    """Real reduced model: the float64 twin of the blocked kernel (half the shared memory, a quarter of the flops)."""
+    ops = [o for o in (a0s, a1s, a2s) if o is not None]
+    r, m = br.shape
+    lda = ops[0].stride(0)
+    if any(o.stride(0) != lda or o.shape != (r, r) for o in ops):
+        raise ValueError("sweep: operators must share shape (r, r) and leading dimension")
+    nf = int(c0.numel())
+    dev = br.device
+    x = torch.empty((nf, r, m), dtype=F64, device=dev) if want_x else None
+    gsm_ = torch.empty((nf, m, m), dtype=C128, device=dev) if want_gsm else None
+    info = torch.zeros(nf, dtype=torch.int32, device=dev)
+    flops_pt = (2.0 / 3.0) * r ** 3 + 2.0 * r * r * m + 4.0 * r * r + 2.0 * r * m * m
+    bytes_pt = 16.0 * m * m * (gsm_ is not None) + 8.0 * r * m * (x is not None) + 40.0 + 4.0
+    with _timed("sweep_lu_gsm", nbytes=bytes_pt * nf, flops=flops_pt * nf):
+        _ffi.check(lib.mf_sweep_lu_gsm_f64(_ptr(a0s), _ptr(a1s), _ptr(a2s), lda, _ptr(br), br.stride(0), r, m,
+                                           _ptr(c0), _ptr(c1), _ptr(c2), _ptr(cb), _ptr(zscale), nf, _ptr(x), _ptr(gsm_), _ptr(info), _stream()),
+                   "mf_sweep_lu_gsm_f64")
+    return SweepResult(x, gsm_, info)
 
 
 def gsm(x: torch.Tensor, bmat: torch.Tensor, cb: torch.Tensor, zscale: torch.Tensor) -> torch.Tensor:

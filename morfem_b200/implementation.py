@@ -254,7 +254,7 @@ def error_estimator(md: ModelDefinition, q, opm=None, time_stats=None, _ops: Opt
     res = _sweep_device(md.domain, [a0_r, a1_r, a2_r], b_r, md.t_a0, md.t_a1, md.t_a2, md.t_b, want_x=True, want_gsm=False)
     dom = np.asarray(md.domain, dtype=np.float64)
     c = [torch.from_numpy(coefficient_array(f, dom)).to(qd.device) for f in (md.t_a0, md.t_a1, md.t_a2, md.t_b)]
-    err = dv.estimator(res.x, g, hb, bb, c[0], c[1], c[2], c[3])
+    err = dv.estimator(res.x if res.x.is_complex() else res.x.to(torch.complex128), g, hb, bb, c[0], c[1], c[2], c[3])
     return err.cpu().numpy()
 
 

@@ -285,7 +285,7 @@ def test_real_float64_stages_equal_the_complex_path(dv):
     qc, rc, bc, _ = dv.basis_and_projection(dv.to_device_c128(snaps), ops.project_block)
     qr, rr, br, info = dv.basis_and_projection(dv.real_or_complex_to_device(snaps), ops.project_block)
     torch.cuda.synchronize()
-    assert qr.dtype == torch.float64 and rr[0].dtype == torch.complex128
+    assert qr.dtype == torch.float64 and rr[0].dtype == torch.float64 and br.dtype == torch.float64
     assert orc.subspace_residual(qc.cpu().numpy().real, qr.cpu().numpy()) < 1e-9
     # reduced operators live in each run's own basis; the S-parameters are basis invariant
     f = g["f"]

@@ -191,3 +191,55 @@ def test_sweep_large_batch_property(dv):
     s = res.gsm.cpu().numpy()
     unit = np.einsum("fij,fkj->fik", s, s.conj())
     assert np.abs(unit - np.eye(m)).max() < 1e-6
+
+
+# ---------------------------------------------------------------------------------- real float64 twin (row N2)
+def run_sweep_real(dv, f, a0, a1, a2, b, cb, want_x=True, want_gsm=True):
+    from scipy.constants import pi, epsilon_0
+    dev = dv.require_cuda()
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(dev)  # noqa: E731
+    ops = [None if (a is None or not np.any(a)) else dv.symmetrize(t(a)) for a in (a0, a1, a2)]
+    res = dv.sweep(ops[0], ops[1], ops[2], t(b), t(np.ones_like(f)), t(f), t(f ** 2), t(cb), t(2 * pi * f * epsilon_0), want_x=want_x, want_gsm=want_gsm)
+    torch.cuda.synchronize()
+    return res
+
+
+@pytest.mark.parametrize("name", REDUCED)
+def test_real_sweep_matches_live_reference_fixture(dv, name):
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    f = g["f"]
+    cb = np.array([orc.b_coefficient(t) for t in f])
+    res = run_sweep_real(dv, f, g["a0"], g["a1"], g["a2"], g["b"], cb)
+    r, m = g["b"].shape
+    from morfem_b200 import _ffi
+    expect_real = bool(_ffi.load().mf_sweep_f64_supported(r, m))
+    assert (res.x.dtype == torch.float64) == expect_real          # larger models fall back to the complex128 kernels
+    x = res.x.cpu().numpy()
+    tol = np.maximum(1e-10, 20 * EPS * g["cond"])
+    assert not np.any(res.info.cpu().numpy())
+    assert np.all(per_point_rel(x.real, g["x"]) < tol) and np.all(per_point_rel(res.gsm.cpu().numpy(), g["gsm"]) < tol)
+
+
+@pytest.mark.parametrize("r,m,nf", [(1, 1, 3), (7, 3, 33), (16, 16, 9), (31, 5, 40), (64, 2, 500), (100, 8, 12), (128, 4, 6)])
+def test_real_sweep_equals_complex_sweep_and_oracle(dv, r, m, nf):
+    from morfem_b200 import synthetic
+    a0, a1, a2, b = synthetic.reduced_model(r, m, seed=100 + r)
+    f = np.linspace(3e9, 5e9, nf)
+    tb = orc.b_coefficient
+    cb = np.array([tb(t) for t in f])
+    real = run_sweep_real(dv, f, a0, a1, a2, b, cb)
+    cplx = run_sweep(dv, f, a0, a1, a2, b, cb, variant=3)
+    assert real.x.dtype == torch.float64
+    assert np.all(per_point_rel(real.x.cpu().numpy(), cplx.x.cpu().numpy().real) < 1e-12)       # same algorithm, same pivots
+    assert np.all(per_point_rel(real.gsm.cpu().numpy(), cplx.gsm.cpu().numpy()) < 1e-12)
+    x_ref = orc.reduced_sweep(f, a0, a1, a2, b, lambda t: 1.0, lambda t: t, lambda t: t ** 2, tb)
+    cond = np.array([np.linalg.cond(orc.system_matrix(1.0, t, t ** 2, a0, a1, a2)) for t in f])
+    assert np.all(per_point_rel(real.x.cpu().numpy(), x_ref) < np.maximum(1e-10, 20 * EPS * cond))
+
+
+def test_real_sweep_reports_singular_points(dv):
+    r, m = 20, 2
+    a0 = np.eye(r)
+    a0[11, 11] = 0.0
+    res = run_sweep_real(dv, np.array([3e9, 4e9]), a0, None, None, np.ones((r, m)), np.ones(2), want_gsm=False)
+    assert list(res.info.cpu().numpy()) == [12, 12]
