@@ -196,8 +196,12 @@ def run_b200(args, wl, rank, world, local_rank):
     cb = impl.coefficient_array(th.b_coefficient, f)
     coeffs = [np.ones_like(f), f, f ** 2, cb, 2 * pi * f * epsilon_0]
     path = mfd.ShardedHotPath([in_c, csc_array(in_c.shape), in_gamma], in_b, n, f.size, coeffs)
-    real = args.dtype == "f64"
-    s_dev = dv.real_or_complex_to_device(s_loc, dev, widen=not real)      # c128 (north star) unless --dtype f64
+    # "c128" (default, the north star's arithmetic): the real synthetic data embedded in complex128, complex128 kernels
+    # throughout.  The synthetic operators and snapshots are real, like the reference's data (main.py:21-23), so "auto" /
+    # "f64" run the real float64 twins -- what the public API selects by itself for such inputs; the default run times
+    # that path too and reports it under "other_dtype".
+    real = args.dtype in ("auto", "f64")
+    s_dev = dv.real_or_complex_to_device(s_loc, dev, widen=not real)
     f_total = f.size
 
     def barrier():
@@ -240,6 +244,37 @@ def run_b200(args, wl, rank, world, local_rank):
     ms_total = float(t.item())
     ms_step = ms_total / args.steps
     value = f_total / (ms_step * 1e-3)
+
+    # ---- the same timed loop on the other arithmetic type (same data; complex128 kernels <-> real float64 twins)
+    alt = None
+    if not args.no_alt_dtype:
+        s_alt = dv.real_or_complex_to_device(s_loc, dev, widen=real)
+
+        def step_alt():
+            if use_graph:
+                return path.step_graph(s_alt, want_x=False)
+            return path.step(s_alt, want_x=False, gather=True)
+
+        for _ in range(max(args.warmup, 3)):
+            step_alt()
+        barrier()
+        a0_, a1_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0_.record()
+        for _ in range(args.steps):
+            step_alt()
+        a1_.record()
+        barrier()
+        ta = torch.tensor([a0_.elapsed_time(a1_)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ta, op=dist.ReduceOp.MAX)
+        ms_alt = float(ta.item()) / args.steps
+        if use_graph and path.verify() is not None:
+            raise SystemExit("bench: optimistic CholeskyQR2 failed verification (alternate dtype)")
+        alt = {"dtype": "c128" if real else "f64", "value": f_total / (ms_alt * 1e-3), "unit": UNIT, "ms_per_step": ms_alt,
+               "note": "same workload and timed loop on the other arithmetic type: " +
+                       ("real data embedded in complex128, complex128 kernels throughout (the north star's kernels)" if real
+                        else "real float64 twins of every kernel")}
+        del s_alt
 
     # ---- per-kernel and per-stage timing (CUDA events on the launching stream, separate pass over the same steps)
     prof_steps = max(1, min(args.steps, 5))
@@ -286,12 +321,12 @@ def run_b200(args, wl, rank, world, local_rank):
         if t_flop >= t_mem:
             ach = a["flops"] / a["calls"] / (ms_call * 1e-3) / 1e12
             roof = {"kernel": dominant, "bound": "tensor", "achieved": ach, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": ach / FP64_PEAK_TFLOPS,
-                    "traffic": (traffic.get(dominant) or {}).get("bytes") if args.workload == "cfg2" else None, "peak_source": "FP64 tensor-pipe (DMMA) peak measured on this pool's B200 by tools/fp64_peaks.cu; "
+                    "traffic": (traffic.get(dominant) or {}).get("bytes") if (args.workload == "cfg2" and not real) else None, "peak_source": "FP64 tensor-pipe (DMMA) peak measured on this pool's B200 by tools/fp64_peaks.cu; "
                                                     "MEASURED_PEAKS.json holds no FP64 figure and its bf16 figure does not bound an FP64 kernel", **share}
         else:
             ach = a["bytes"] / a["calls"] / (ms_call * 1e-3) / 1e9
             roof = {"kernel": dominant, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
-                    "traffic": (traffic.get(dominant) or {}).get("bytes") if args.workload == "cfg2" else None,
+                    "traffic": (traffic.get(dominant) or {}).get("bytes") if (args.workload == "cfg2" and not real) else None,
                     "peak_source": peak_src, **share}
 
     # ---- end to end through the reference-facing call, host (pinned) buffers in, host array out (rank-local job)
@@ -364,6 +399,7 @@ def run_b200(args, wl, rank, world, local_rank):
                            "l2": "inputs larger than L2 (snapshot block %.0f MB + operators per GPU); no flush" % (s_dev.numel() * s_dev.element_size() / 1e6),
                            "parallelism": "rows of Q/operators and sweep points block-sharded over %d GPU(s)" % world},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu_baseline,
+                "other_dtype": alt,
                 "stages": {"basis_plus_projection_ms": stage_ms["basis_plus_projection"], "sweep_ms": stage_ms["sweep"],
                            "gather_ms": stage_ms["gather"],
                            "sweep_kernel_points_per_s_per_gpu": (f_total / world) / (sweep_k["ms_per_step"] * 1e-3) if sweep_k.get("ms_per_step") else None},
@@ -382,9 +418,10 @@ def main():
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--cpu-points", type=int, default=2000, help="sweep points the CPU arm solves per step (scaled to the full axis)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--dtype", default="c128", choices=["c128", "f64"],
+    ap.add_argument("--dtype", default="c128", choices=["auto", "c128", "f64"],
                     help="c128: complex128 kernels throughout (north star); f64: the real float64 twins (the reference's own dtype; "
                          "valid because the synthetic operators and snapshots are real, like the reference's data)")
+    ap.add_argument("--no-alt-dtype", action="store_true", help="skip the second timed loop on the other arithmetic type")
     ap.add_argument("--no-graph", action="store_true", help="run the eager (adaptive CholeskyQR) step instead of the CUDA-graph replay at N=1")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]

@@ -199,7 +199,7 @@ class ShardedHotPath:
         replay."""
         if self.world > 1:
             raise RuntimeError("step_graph is single-rank; use step() under torchrun")
-        key = (tuple(s_local.shape), bool(want_x))
+        key = (tuple(s_local.shape), s_local.dtype, bool(want_x))
         if self._graph is None or self._graph["key"] != key:
             static_s = s_local.clone()
             for _ in range(2):                                   # warm-up: workspaces, function attributes, side stream
