@@ -215,7 +215,7 @@ def run_b200(args, wl, rank, world, local_rank):
     def step():
         if use_graph:
             return path.step_graph(s_dev, want_x=False)       # whole step replayed from one CUDA graph
-        return path.step(s_dev, want_x=False, gather=True)
+        return path.step_deferred(s_dev, want_x=False, gather=True)   # eager launches, CholeskyQR2 flags verified after the loop
 
     for _ in range(max(args.warmup, 3)):
         out = step()
@@ -232,6 +232,8 @@ def run_b200(args, wl, rank, world, local_rank):
     barrier()
     clocks = sampler.stop()
     launches = _ffi.launch_count() - launches0
+    if not use_graph and not path.verify_deferred():
+        raise SystemExit("bench: optimistic CholeskyQR2 failed verification on the synthetic snapshot block")
     if use_graph:
         # a graph replay launches the captured kernels without passing through the C ABI's counter
         launches = args.steps * path.launches_per_graph
@@ -253,7 +255,7 @@ def run_b200(args, wl, rank, world, local_rank):
         def step_alt():
             if use_graph:
                 return path.step_graph(s_alt, want_x=False)
-            return path.step(s_alt, want_x=False, gather=True)
+            return path.step_deferred(s_alt, want_x=False, gather=True)
 
         for _ in range(max(args.warmup, 3)):
             step_alt()
@@ -268,7 +270,7 @@ def run_b200(args, wl, rank, world, local_rank):
         if world > 1:
             dist.all_reduce(ta, op=dist.ReduceOp.MAX)
         ms_alt = float(ta.item()) / args.steps
-        if use_graph and path.verify() is not None:
+        if (use_graph and path.verify() is not None) or (not use_graph and not path.verify_deferred()):
             raise SystemExit("bench: optimistic CholeskyQR2 failed verification (alternate dtype)")
         alt = {"dtype": "c128" if real else "f64", "value": f_total / (ms_alt * 1e-3), "unit": UNIT, "ms_per_step": ms_alt,
                "note": "same workload and timed loop on the other arithmetic type: " +

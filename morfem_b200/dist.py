@@ -111,7 +111,7 @@ def exchange_halo(q_local: torch.Tensor, plan: HaloPlan, out: Optional[torch.Ten
     peer and direction)."""
     r = q_local.shape[1]
     nwin = plan.win1 - plan.win0
-    if out is None or out.shape[0] < nwin or out.shape[1] != r:
+    if out is None or out.shape[0] < nwin or out.shape[1] != r or out.dtype != q_local.dtype or out.device != q_local.device:
         out = torch.empty((nwin, r), dtype=q_local.dtype, device=q_local.device)
     win = out[:nwin]
     win[plan.row0 - plan.win0:plan.row1 - plan.win0].copy_(q_local)
@@ -182,6 +182,7 @@ class ShardedHotPath:
         self.stage_events = None     # bench.py: set to a list to collect per-stage CUDA events
         self._graph = None           # (CUDAGraph, static input, static outputs, pinned flag buffer) of step_graph
         self.launches_per_graph = 0
+        self._pending = []           # device flag blocks of step_deferred calls awaiting verify_deferred
 
 
     def _mark(self, ev):
@@ -219,6 +220,20 @@ class ShardedHotPath:
         gr["graph"].replay()
         gr["flags_host"].copy_(gr["out"][4].flags, non_blocking=True)
         return gr["out"][:4]
+
+    def step_deferred(self, s_local: torch.Tensor, want_x: bool = False, gather: bool = True):
+        """Eager ``step`` with the optimistic CholeskyQR2 (no device->host read inside the step, so the launch queue never
+        drains): the success flags of every call are kept and checked by ``verify_deferred()``.  Works under torchrun."""
+        out = self.step(s_local, want_x=want_x, gather=gather, optimistic=True)
+        self._pending.append(out[4].flags)
+        return out[:4]
+
+    def verify_deferred(self) -> bool:
+        """Synchronise and check the flags of all ``step_deferred`` calls since the last check (all ranks agree: the
+        Gram matrices are all-reduced, every rank factors the same matrix).  False = redo those steps with ``step``."""
+        ok = all(self.dv.flags_ok(f.cpu()) for f in self._pending)
+        self._pending = []
+        return ok
 
     def verify(self):
         """Synchronise and check the deferred flags of the last ``step_graph``; on failure return the results of the

@@ -89,3 +89,17 @@ def test_sharded_steps_over_gloo(tmp_path, world, f_total):
     port = _free_port()
     mp.spawn(_worker, args=(world, port, (3, 2, 30), 5, f_total, str(tmp_path)), nprocs=world, join=True)
     assert all(os.path.exists(tmp_path / f"ok{r}") for r in range(world))
+
+
+def test_halo_window_buffer_is_not_reused_across_dtypes():
+    """The window buffer is cached between steps; a float64 step after a complex128 step (bench.py times both) must get
+    its own buffer instead of silently writing real rows into a complex window."""
+    import torch
+    from morfem_b200 import dist as mfd
+    plan = mfd.build_halo_plan(0, 1, 10, [(0, 10)])
+    qc = torch.randn(10, 3, dtype=torch.complex128)
+    win_c = mfd.exchange_halo(qc, plan)
+    qr = torch.randn(10, 3, dtype=torch.float64)
+    win_r = mfd.exchange_halo(qr, plan, out=win_c)
+    assert win_r.dtype == torch.float64 and torch.equal(win_r, qr)
+    assert torch.equal(mfd.exchange_halo(qc, plan, out=win_c), qc)
