@@ -421,6 +421,67 @@ class BasisInfo:
         return self._sweeps
 
 
+
+# ------------------------------------------------------------------ blocked r x r Cholesky / triangular inverse (r > 112)
+_SMALL_NB = 64      # block size: the diagonal blocks run on the single-CTA shared-memory kernels
+
+
+def _potrf_upper(g: torch.Tensor, info: torch.Tensor) -> None:
+    """In-place Cholesky ``G = R^H R`` (R upper) with ``info`` = 0 or the 1-based failing column.  Up to r = 112 one
+    shared-memory kernel; above that a right-looking blocked factorisation whose diagonal blocks use that kernel and
+    whose panel / trailing updates are small DMMA contractions (the one-CTA global-memory kernel needs ~3 ms at r = 256,
+    this ~0.4 ms)."""
+    lib = _ffi.load()
+    r = g.shape[0]
+    if r <= 112:
+        _ffi.check(lib.mf_potrf_upper_c128(_ptr(g), g.stride(0), r, _ptr(info), _stream()), "mf_potrf_upper_c128")
+        return
+    nblk = (r + _SMALL_NB - 1) // _SMALL_NB
+    infos = torch.zeros(nblk, dtype=torch.int32, device=g.device)
+    for b, j0 in enumerate(range(0, r, _SMALL_NB)):
+        j1 = min(j0 + _SMALL_NB, r)
+        gjj = g[j0:j1, j0:j1]
+        _ffi.check(lib.mf_potrf_upper_c128(_ptr(gjj), g.stride(0), j1 - j0, _ptr(infos[b:]), _stream()), "mf_potrf_upper_c128")
+        if j1 < r:
+            rinv11 = torch.empty((j1 - j0, j1 - j0), dtype=C128, device=g.device)
+            _ffi.check(lib.mf_trtri_upper_c128(_ptr(gjj), g.stride(0), j1 - j0, _ptr(rinv11), rinv11.stride(0), _stream()), "mf_trtri_upper_c128")
+            r12 = gemm_tn(rinv11, g[j0:j1, j1:].contiguous(), conj=True)          # R12 = R11^-H G12
+            g[j0:j1, j1:] = r12
+            g[j1:, j1:] -= gemm_tn(r12, r12, conj=True)                          # G22 -= R12^H R12
+    g.triu_()
+    # first failing block decides (LAPACK info convention, offset by the block start)
+    starts = torch.arange(0, r, _SMALL_NB, dtype=torch.int32, device=g.device)
+    bad = infos != 0
+    first = torch.where(bad, starts + infos, torch.full_like(infos, 2 ** 30)).min()
+    info.copy_(torch.where(bad.any(), first, torch.zeros_like(first)).reshape(1).to(torch.int32))
+
+
+def _trtri_upper(rm: torch.Tensor) -> torch.Tensor:
+    """``R^-1`` of an upper-triangular matrix: shared-memory kernel up to r = 96, above that the 2 x 2 block recursion
+    ``[[A, B], [0, C]]^-1 = [[A^-1, -A^-1 B C^-1], [0, C^-1]]`` on top of it."""
+    lib = _ffi.load()
+    r = rm.shape[0]
+    out = torch.zeros((r, r), dtype=C128, device=rm.device)
+
+    def rec(lo: int, hi: int) -> None:
+        n = hi - lo
+        if n <= 96:
+            blk = rm[lo:hi, lo:hi]
+            tgt = out[lo:hi, lo:hi]
+            _ffi.check(lib.mf_trtri_upper_c128(_ptr(blk), rm.stride(0), n, _ptr(tgt), out.stride(0), _stream()), "mf_trtri_upper_c128")
+            return
+        mid = lo + (n // 2 + _SMALL_NB - 1) // _SMALL_NB * _SMALL_NB
+        rec(lo, mid)
+        rec(mid, hi)
+        t = gemm_nn(out[lo:mid, lo:mid].contiguous(), rm[lo:mid, mid:hi].contiguous())     # A^-1 B
+        out[lo:mid, mid:hi] = -gemm_nn(t, out[mid:hi, mid:hi].contiguous())                 # -(A^-1 B) C^-1
+
+    if r <= 96:
+        _ffi.check(lib.mf_trtri_upper_c128(_ptr(rm), rm.stride(0), r, _ptr(out), out.stride(0), _stream()), "mf_trtri_upper_c128")
+    else:
+        rec(0, r)
+    return out
+
 @dataclass
 class CholQR:
     """Result of the Cholesky-QR passes: ``S = x @ r_tot`` with ``x @ rinv`` orthonormal to rounding
@@ -460,10 +521,9 @@ def _cholesky_qr2_optimistic(s: torch.Tensor, group=None) -> CholQR:
         stats = flags[p, :16].view(torch.float64)
         info = flags[p, 16:20].view(torch.int32)
         _ffi.check(lib.mf_equilibrate_c128(_ptr(g), g.stride(0), r, 0.0, _ptr(d), _ptr(stats), _stream()), "mf_equilibrate_c128")
-        _ffi.check(lib.mf_potrf_upper_c128(_ptr(g), g.stride(0), r, _ptr(info), _stream()), "mf_potrf_upper_c128")
+        _potrf_upper(g, info)
         _ffi.check(lib.mf_scale_cols_c128(_ptr(g), g.stride(0), r, r, _ptr(d), -1, _stream()), "mf_scale_cols_c128")
-        rinv = torch.empty((r, r), dtype=C128, device=dev)
-        _ffi.check(lib.mf_trtri_upper_c128(_ptr(g), g.stride(0), r, _ptr(rinv), rinv.stride(0), _stream()), "mf_trtri_upper_c128")
+        rinv = _trtri_upper(g)
         r_tot = g if r_tot is None else gemm_nn(g, r_tot)
         if p == 0:
             x = gemm_nn(x, _like_block(rinv, x))
@@ -498,7 +558,7 @@ def cholesky_qr(s: torch.Tensor, group=None, max_passes: int = 6, optimistic: bo
         while True:
             gw = g.clone()
             _ffi.check(lib.mf_equilibrate_c128(_ptr(gw), gw.stride(0), r, shift, _ptr(d), _ptr(stats), _stream()), "mf_equilibrate_c128")
-            _ffi.check(lib.mf_potrf_upper_c128(_ptr(gw), gw.stride(0), r, _ptr(info), _stream()), "mf_potrf_upper_c128")
+            _potrf_upper(gw, info)
             host_flags = flags.cpu()
             if int(host_flags[16:20].view(torch.int32)[0]) == 0:
                 break
@@ -510,8 +570,7 @@ def cholesky_qr(s: torch.Tensor, group=None, max_passes: int = 6, optimistic: bo
         departure = float(host_flags[:8].view(torch.float64)[0])
         # R = Rtilde D^-1 (undo the equilibration), Rinv = R^-1
         _ffi.check(lib.mf_scale_cols_c128(_ptr(gw), gw.stride(0), r, r, _ptr(d), -1, _stream()), "mf_scale_cols_c128")
-        rinv = torch.empty((r, r), dtype=C128, device=dev)
-        _ffi.check(lib.mf_trtri_upper_c128(_ptr(gw), gw.stride(0), r, _ptr(rinv), rinv.stride(0), _stream()), "mf_trtri_upper_c128")
+        rinv = _trtri_upper(gw)
         r_tot = gw if r_tot is None else gemm_nn(gw, r_tot)
         final = (departure < 0.1 and shift == 0.0) or p == max_passes - 1
         if final:

@@ -299,3 +299,25 @@ def test_real_float64_stages_equal_the_complex_path(dv):
     s_auto = th.model_order_reduction_gsm_from_snapshots(f, snaps, in_c, in_gamma, in_b)
     s_cplx = th.model_order_reduction_gsm_from_snapshots(f, snaps, in_c, in_gamma, in_b, real_path=False)
     assert orc.rel_err(s_auto, s_cplx) < 1e-8
+
+
+@pytest.mark.parametrize("r", [113, 130, 200, 256, 300])
+def test_blocked_cholesky_and_inverse_for_large_r(dv, r):
+    """r > 112: the r x r Cholesky and triangular inverse run as blocked drivers over the shared-memory kernels."""
+    rng = np.random.default_rng(r)
+    a = rng.standard_normal((r + 40, r)) + 1j * rng.standard_normal((r + 40, r))
+    g = a.conj().T @ a
+    gd = dv.to_device_c128(g)
+    info = torch.zeros(1, dtype=torch.int32, device="cuda")
+    dv._potrf_upper(gd, info)
+    rinv = dv._trtri_upper(gd)
+    torch.cuda.synchronize()
+    rr = gd.cpu().numpy()
+    assert int(info.item()) == 0 and np.allclose(np.tril(rr, -1), 0)
+    assert orc.rel_err(rr.conj().T @ rr, g) < 1e-13
+    assert orc.rel_err(rinv.cpu().numpy() @ rr, np.eye(r)) < 1e-11
+    bad = g.copy()
+    bad[150 if r > 150 else 100, :] = 0; bad[:, 150 if r > 150 else 100] = 0           # not positive definite from that column on
+    bd = dv.to_device_c128(bad)
+    dv._potrf_upper(bd, info)
+    assert int(info.item()) == (151 if r > 150 else 101)
