@@ -41,7 +41,7 @@ __global__ void equilibrate_kernel(cplx* G, long long ld, int r, double shift, d
 // (r <= POTRF_SMEM_MAX): every step of the factorisation is a dependent access, which costs an L2 round trip each
 // when the matrix stays in global memory.
 constexpr int POTRF_SMEM_MAX = 112;
-constexpr int POTRF_THREADS = 256;
+constexpr int POTRF_THREADS = 1024;
 template <bool SMEM>
 __global__ void __launch_bounds__(POTRF_THREADS) potrf_upper_kernel(cplx* Gg, long long ldg, int r, int* info) {
     extern __shared__ __align__(16) cplx gsm[];
