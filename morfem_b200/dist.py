@@ -254,20 +254,30 @@ class ShardedHotPath:
         ev = [] if self.stage_events is not None else None
         self._mark(ev)
         def project_block(x):
-            """x^T (A_i x) and x^T b for the un-rotated Cholesky-QR block (row partials all-reduced)."""
-            g_list = []
-            for csr, plan in zip(self.ops, self.plans):
-                if csr is None:
-                    g_list.append(None)
-                    continue
-                dv.group_rows(csr, x.shape[1])       # row-grouped operand, built once per operator on first use
+            """x^T (A_i x) and x^T b for the un-rotated Cholesky-QR block.  All row partials land in ONE flat buffer that is
+            all-reduced once; operators with the same halo plan (same sparsity pattern) share one halo exchange."""
+            r = x.shape[1]
+            m = self.b.ncols
+            live = [i for i, csr in enumerate(self.ops) if csr is not None]
+            flat = torch.empty(len(live) * r * r + r * m, dtype=x.dtype, device=x.device)
+            g_list = [None] * len(self.ops)
+            windows = {}
+            for k, i in enumerate(live):
+                csr, plan = self.ops[i], self.plans[i]
+                dv.group_rows(csr, r)                # row-grouped operand, built once per operator on first use
                 if self.world > 1:
-                    self._win = exchange_halo(x, plan, self._win, group)
-                    y = dv.spmm(csr, self._win[:plan.win1 - plan.win0])
+                    key = (plan.win0, plan.win1, tuple(plan.send), tuple(plan.recv))
+                    if key not in windows:
+                        windows[key] = exchange_halo(x, plan, self._win if not windows else None, group)
+                        if len(windows) == 1:
+                            self._win = windows[key]
+                    y = dv.spmm(csr, windows[key][:plan.win1 - plan.win0])
                 else:
                     y = dv.spmm(csr, x)
-                g_list.append(allreduce_sum_(dv.gemm_tn(y, x, conj=False), group))
-            bt = allreduce_sum_(dv.project_rhs(self.b, x, self.row0, conj=False), group)
+                g_list[i] = dv.gemm_tn(y, x, conj=False, out=flat[k * r * r:(k + 1) * r * r].view(r, r))
+            bt = flat[len(live) * r * r:].view(r, m)
+            bt.copy_(dv.project_rhs(self.b, x, self.row0, conj=False))
+            allreduce_sum_(flat, group)
             return g_list, bt
 
         q, reduced, b_r, info = dv.basis_and_projection(s_local, project_block, group=group, optimistic=optimistic)
