@@ -184,30 +184,37 @@ __global__ void __launch_bounds__(ST_NT, 1) sweep_stream_kernel(SweepParams p, i
         const double c0 = p.c0[pt], c1 = p.c1[pt], c2 = p.c2[pt], cb = p.cb[pt];
         // ---- assemble [A(t) | cb Br] into the slot, identity on the padded diagonal ----
         constexpr int RPLA = (NBO == 32) ? 8 : 16;                // row elements per lane (R <= 32 RPLA)
-        for (int i = warp; i < R; i += ST_NW) {
-            cplx* Arow = A + (long long)i * LD;
-            const long long rowoff = (long long)i * p.lda;
-            if (i < r) {
-                cplx v[RPLA];
+        constexpr int RGA = (NBO == 32) ? 2 : 1;                  // operator rows per warp iteration (all their loads in flight)
+        for (int i0 = warp * RGA; i0 < R; i0 += ST_NW * RGA) {
+            cplx v[RGA][RPLA];
+#pragma unroll
+            for (int g2 = 0; g2 < RGA; ++g2) {
+                const int i = i0 + g2;
+                const long long rowoff = (long long)i * p.lda;
 #pragma unroll
                 for (int q = 0; q < RPLA; ++q) {
                     const int j = lane + 32 * q;
-                    v[q] = cmake(0.0, 0.0);
-                    if (j < r) {
-                        if (hasA0) { const cplx x = __ldg(p.A0 + rowoff + j); v[q].x = c0 * x.x; v[q].y = c0 * x.y; }
-                        if (hasA1) { const cplx x = __ldg(p.A1 + rowoff + j); v[q].x = fma(c1, x.x, v[q].x); v[q].y = fma(c1, x.y, v[q].y); }
-                        if (hasA2) { const cplx x = __ldg(p.A2 + rowoff + j); v[q].x = fma(c2, x.x, v[q].x); v[q].y = fma(c2, x.y, v[q].y); }
+                    v[g2][q] = cmake(0.0, 0.0);
+                    if (i < r && j < r) {
+                        if (hasA0) { const cplx x = __ldg(p.A0 + rowoff + j); v[g2][q].x = c0 * x.x; v[g2][q].y = c0 * x.y; }
+                        if (hasA1) { const cplx x = __ldg(p.A1 + rowoff + j); v[g2][q].x = fma(c1, x.x, v[g2][q].x); v[g2][q].y = fma(c1, x.y, v[g2][q].y); }
+                        if (hasA2) { const cplx x = __ldg(p.A2 + rowoff + j); v[g2][q].x = fma(c2, x.x, v[g2][q].x); v[g2][q].y = fma(c2, x.y, v[g2][q].y); }
+                    } else if (i == j) v[g2][q].x = 1.0;          // identity on the padded diagonal
+                }
+            }
+#pragma unroll
+            for (int g2 = 0; g2 < RGA; ++g2) {
+                const int i = i0 + g2;
+                if (i < R) {
+                    cplx* Arow = A + (long long)i * LD;
+#pragma unroll
+                    for (int q = 0; q < RPLA; ++q) { const int j = lane + 32 * q; if (j < R) Arow[j] = v[g2][q]; }
+                    for (int j = lane; j < LD - R; j += 32) {
+                        cplx b = cmake(0.0, 0.0);
+                        if (i < r && j < m) { const cplx x = __ldg(p.Br + (long long)i * p.ldb + j); b.x = cb * x.x; b.y = cb * x.y; }
+                        Arow[R + j] = b;
                     }
                 }
-#pragma unroll
-                for (int q = 0; q < RPLA; ++q) { const int j = lane + 32 * q; if (j < R) Arow[j] = v[q]; }
-                for (int j = lane; j < LD - R; j += 32) {
-                    cplx b = cmake(0.0, 0.0);
-                    if (j < m) { const cplx x = __ldg(p.Br + (long long)i * p.ldb + j); b.x = cb * x.x; b.y = cb * x.y; }
-                    Arow[R + j] = b;
-                }
-            } else {
-                for (int j = lane; j < LD; j += 32) Arow[j] = cmake(j == i ? 1.0 : 0.0, 0.0);
             }
         }
         if (tid == 0) *info_sh = 0;
@@ -374,37 +381,72 @@ __global__ void __launch_bounds__(ST_NT, 1) sweep_stream_kernel(SweepParams p, i
             }
         }
 
-        // ---- back substitution U x = y, row oriented, one warp per right-hand side; x in shared memory (PB area) ----
+        // ---- back substitution U x = y in blocks of 8 rows; y / x (R x m) live in shared memory (PB area) ----
+        // Per block: lanes 0..m-1 of warp 0 solve the 8 x 8 triangular system (diagonal block staged in shared memory),
+        // then every thread updates ITS row(s) above the block with the 8 new unknowns.  The 128-byte row segments of U and
+        // the next diagonal block are prefetched into registers one block ahead, so the dependent chain per block is the
+        // small solve plus two CTA barriers -- no DRAM round trip.
         cplx* xs = PB;                                            // R x m, xs[k * m + c]
-        constexpr int RPL = (NBO == 32) ? 8 : 16;                 // row elements per lane (R <= 32 RPL)
-        for (int c = warp; c < m; c += ST_NW) {
-            cplx cur[RPL], nxt[RPL], ydg[2], ydn[2];
-            {
-                const cplx* urow = A + (long long)(R - 1) * LD;
+        cplx* dblk = UB;                                          // 8 x 8 diagonal block (row-major)
+        constexpr int RPT = (NBO == 32) ? 1 : 2;                  // rows per thread (R <= 256 RPT)
+        for (int e = tid; e < R * m; e += ST_NT) { const int i = e / m, c = e - i * m; xs[e] = A[(long long)i * LD + R + c]; }
+        cplx un[RPT][8], dn = cmake(0.0, 0.0);
+        {
+            const int kb8 = R - 8;
 #pragma unroll
-                for (int i = 0; i < RPL; ++i) { const int j = lane + 32 * i; cur[i] = j < R ? urow[j] : cmake(0.0, 0.0); }
-                ydg[0] = urow[R + c]; ydg[1] = urow[R - 1];
+            for (int s = 0; s < RPT; ++s) {
+                const int i = tid + ST_NT * s;
+                const cplx* src = A + (long long)i * LD + kb8;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) un[s][j] = (i < kb8) ? src[j] : cmake(0.0, 0.0);
             }
-            for (int k = R - 1; k >= 0; --k) {
-                if (k > 0) {                                      // prefetch row k-1 while row k is reduced
-                    const cplx* urow = A + (long long)(k - 1) * LD;
+            if (tid < 64) dn = A[(long long)(kb8 + (tid >> 3)) * LD + kb8 + (tid & 7)];
+        }
+        for (int kb8 = R - 8; kb8 >= 0; kb8 -= 8) {
+            cplx uc[RPT][8];
 #pragma unroll
-                    for (int i = 0; i < RPL; ++i) { const int j = lane + 32 * i; nxt[i] = j < R ? urow[j] : cmake(0.0, 0.0); }
-                    ydn[0] = urow[R + c]; ydn[1] = urow[k - 1];
+            for (int s = 0; s < RPT; ++s)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) uc[s][j] = un[s][j];
+            if (tid < 64) dblk[tid] = dn;
+            if (kb8 >= 8) {                                       // prefetch the next block (one block above)
+                const int nb8 = kb8 - 8;
+#pragma unroll
+                for (int s = 0; s < RPT; ++s) {
+                    const int i = tid + ST_NT * s;
+                    const cplx* src = A + (long long)i * LD + nb8;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) un[s][j] = (i < nb8) ? src[j] : cmake(0.0, 0.0);
                 }
-                cplx acc = cmake(0.0, 0.0);
+                if (tid < 64) dn = A[(long long)(nb8 + (tid >> 3)) * LD + nb8 + (tid & 7)];
+            }
+            __syncthreads();                                      // dblk and the y values of this block are in place
+            if (tid < m) {
+                const int c = tid;
+                cplx x[8];
 #pragma unroll
-                for (int i = 0; i < RPL; ++i) { const int j = lane + 32 * i; if (j > k && j < R) cfma(acc, cur[i], xs[j * m + c]); }
+                for (int j = 0; j < 8; ++j) x[j] = xs[(kb8 + j) * m + c];
 #pragma unroll
-                for (int off = 16; off > 0; off >>= 1) {
-                    acc.x += __shfl_xor_sync(FULL, acc.x, off);
-                    acc.y += __shfl_xor_sync(FULL, acc.y, off);
+                for (int j = 7; j >= 0; --j) {
+#pragma unroll
+                    for (int jj = j + 1; jj < 8; ++jj) cfms(x[j], dblk[j * 8 + jj], x[jj]);
+                    x[j] = cmul(x[j], dblk[j * 8 + j]);           // reciprocal pivot on the diagonal
                 }
-                if (lane == 0) xs[k * m + c] = cmul(cmake(ydg[0].x - acc.x, ydg[0].y - acc.y), ydg[1]);   // ydg[1] = reciprocal pivot
-                __syncwarp();
 #pragma unroll
-                for (int i = 0; i < RPL; ++i) cur[i] = nxt[i];
-                ydg[0] = ydn[0]; ydg[1] = ydn[1];
+                for (int j = 0; j < 8; ++j) xs[(kb8 + j) * m + c] = x[j];
+            }
+            __syncthreads();
+#pragma unroll
+            for (int s = 0; s < RPT; ++s) {
+                const int i = tid + ST_NT * s;
+                if (i < kb8) {
+                    for (int c = 0; c < m; ++c) {
+                        cplx y = xs[i * m + c];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) cfms(y, uc[s][j], xs[(kb8 + j) * m + c]);
+                        xs[i * m + c] = y;
+                    }
+                }
             }
         }
         __syncthreads();
