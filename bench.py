@@ -34,6 +34,9 @@ WORKLOADS = {
     "cfg3": dict(grid=(25, 20, 250), r=256, m=4, f=12500,
                  desc="BASELINE configs[2]: synthetic N=1M DOF, r=256, 4 ports, 100k freq points sharded across 8 B200 "
                       "(per GPU: 125k rows, 12.5k points; weak scaling below 8 GPUs)"),
+    "cfg5": dict(grid=(25, 20, 1000), r=512, m=8, f=125000,
+                 desc="BASELINE configs[4]: dense wideband sweep N=4M DOF, r=512, 8 ports, 1M freq points, row-sharded projection "
+                      "(per GPU at 8 GPUs: 500k rows, 125k points; weak scaling below 8 GPUs)"),
     "small": dict(grid=(5, 4, 100), r=16, m=2, f=500, desc="smoke-sized workload"),
 }
 METRIC = "reduced-sweep freq points/sec"
