@@ -230,10 +230,12 @@ transfer_bytes = {"h2d": 0, "d2h": 0}
 
 
 def upload(arr: np.ndarray, device) -> torch.Tensor:
-    """One host->device copy of a contiguous ndarray (no dtype conversion, no intermediate host copy)."""
+    """One host->device copy of a contiguous ndarray (no dtype conversion, no intermediate host copy).  The copy is queued
+    on the current stream; from pinned memory it is asynchronous, so consecutive uploads and the first kernels overlap
+    with the host work between them (every public call ends with a blocking download, which orders it before return)."""
     t = torch.from_numpy(arr)
     transfer_bytes["h2d"] += t.numel() * t.element_size()
-    return t.to(device, non_blocking=False)
+    return t.to(device, non_blocking=True)
 
 
 def download(t: torch.Tensor, out: Optional[torch.Tensor] = None) -> np.ndarray:
@@ -289,7 +291,7 @@ def group_rows(a: DeviceCSR, r: int) -> None:
     _ffi.check(lib.mf_spmm_group_count(_ptr(a.rowptr), _ptr(a.colidx), a.nrows, g, _ptr(counts), _stream()), "mf_spmm_group_count")
     ustart = torch.zeros(ngroups + 1, dtype=torch.int64, device=dev)
     torch.cumsum(counts, 0, out=ustart[1:])
-    total = int(ustart[-1].item())
+    total = a.nnz          # capacity: a union is never larger than the rows' non-zero count (no device->host read needed)
     ucols = torch.empty(total, dtype=torch.int32, device=dev)
     uvals = torch.empty(total * g, dtype=torch.float64, device=dev)
     _ffi.check(lib.mf_spmm_group_fill(_ptr(a.rowptr), _ptr(a.colidx), _ptr(a.vals), a.nrows, g, _ptr(ustart), _ptr(ucols), _ptr(uvals),
@@ -310,13 +312,14 @@ def spmm(a: DeviceCSR, q: torch.Tensor, out: Optional[torch.Tensor] = None, col_
     w = 8.0 if real else 16.0
     if a.grouped is not None and col_offset == 0 and a.grouped[0] == int(lib.mf_spmm_group_size(r)):
         g, ustart, ucols, uvals = a.grouped
+        nunion = (int(ustart[-1].item()) if timer is not None else 0)      # only the profiling pass needs the exact size
         if real:
-            nbytes = ucols.numel() * (4.0 + 8.0 * g) + 8.0 * ustart.numel() + w * r * (a.nrows + q.shape[0])
+            nbytes = nunion * (4.0 + 8.0 * g) + 8.0 * ustart.numel() + w * r * (a.nrows + q.shape[0])
             with _timed("spmm_csr", nbytes=nbytes, flops=2.0 * a.nnz * r):
                 _ffi.check(lib.mf_spmm_grouped_f64(_ptr(ustart), _ptr(ucols), _ptr(uvals), a.nrows, g, _ptr(q), q.stride(0), r,
                                                    _ptr(out), out.stride(0), _stream()), "mf_spmm_grouped_f64")
             return out
-        nbytes = ucols.numel() * (4.0 + 8.0 * g) + 8.0 * ustart.numel() + 16.0 * r * (a.nrows + q.shape[0])
+        nbytes = nunion * (4.0 + 8.0 * g) + 8.0 * ustart.numel() + 16.0 * r * (a.nrows + q.shape[0])
         with _timed("spmm_csr", nbytes=nbytes, flops=4.0 * a.nnz * r):
             _ffi.check(lib.mf_spmm_grouped_c128(_ptr(ustart), _ptr(ucols), _ptr(uvals), a.nrows, g, _ptr(q), q.stride(0), r,
                                                 _ptr(out), out.stride(0), _stream()), "mf_spmm_grouped_c128")
@@ -635,6 +638,16 @@ def orthonormalize(s: torch.Tensor, truncation_tol: float = 0.0, group=None, n_g
 
 
 _side_streams = {}
+_upload_streams = {}
+
+
+def upload_stream(dev) -> "torch.cuda.Stream":
+    """Per-device stream for host->device copies that should overlap with compute on the current stream."""
+    st = _upload_streams.get(str(dev))
+    if st is None:
+        st = _upload_streams[str(dev)] = torch.cuda.Stream(device=dev)
+    return st
+
 
 
 def basis_and_projection(s: torch.Tensor, project_block, group=None, truncation_tol: float = 0.0, optimistic: bool = False):

@@ -124,17 +124,34 @@ def _real_inputs(*arrs) -> bool:
 class _DeviceOperators:
     """Full-order operators uploaded once: CSR views for the SpMMs, CSC port matrix."""
 
-    def __init__(self, md: ModelDefinition):
+    def __init__(self, md: ModelDefinition, side_stream: bool = False, group_for_r: Optional[int] = None):
+        """``side_stream=True`` queues the uploads (and, with ``group_for_r``, the row grouping) on a separate CUDA stream so
+        that they overlap with whatever the caller runs on the current stream in the meantime (the Cholesky-QR passes only
+        need the snapshot block); the first projection waits for them."""
         from . import device as dv
+        import torch
         self.dv = dv
         self.dev = dv.require_cuda()
         self.ops = [md.a0, md.a1, md.a2]
         self.zero = [_is_zero_operator(a) for a in self.ops]
-        # CSR of a^T == CSC arrays of a: what `q_t @ a` multiplies by (implementation.py:181-183)
-        self.at = [None if z else dv.csr_of_transpose(a, self.dev) for a, z in zip(self.ops, self.zero)]
+        self._ready = None
+        stream = dv.upload_stream(self.dev) if side_stream else torch.cuda.current_stream()
+        with torch.cuda.stream(stream):
+            # CSR of a^T == CSC arrays of a: what `q_t @ a` multiplies by (implementation.py:181-183)
+            self.at = [None if z else dv.csr_of_transpose(a, self.dev, group_for_r=group_for_r) for a, z in zip(self.ops, self.zero)]
+            self.b = dv.csc_to_device(md.b, self.dev)
+            if side_stream:
+                self._ready = torch.cuda.Event()
+                self._ready.record(stream)
         self._a = [None, None, None]   # CSR of a itself, built lazily for the estimator (a_i @ q)
-        self.b = dv.csc_to_device(md.b, self.dev)
         self.b_host = csc_array(md.b)
+
+    def wait_ready(self):
+        """Make the current stream wait for side-stream uploads (no-op otherwise)."""
+        if self._ready is not None:
+            import torch
+            torch.cuda.current_stream().wait_event(self._ready)
+            self._ready = None
 
     def a_csr(self, i):
         if self._a[i] is None and not self.zero[i]:
@@ -145,6 +162,7 @@ class _DeviceOperators:
     def project_block(self, x):
         """``x^T (a_i x)`` for every operator and ``x^T b`` -- the callback of ``device.basis_and_projection``."""
         dv = self.dv
+        self.wait_ready()
         for at in self.at:
             if at is not None:
                 dv.group_rows(at, x.shape[1])
@@ -154,6 +172,7 @@ class _DeviceOperators:
     def project(self, q):
         """Stage 2 (implementation.py:180-184): returns device (a0_r, a1_r, a2_r, b_r); zero operators give zeros."""
         dv = self.dv
+        self.wait_ready()
         r = q.shape[1]
         out = []
         for at, z in zip(self.at, self.zero):

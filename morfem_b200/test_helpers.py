@@ -139,21 +139,24 @@ def model_order_reduction_gsm_from_snapshots(frequency_points, snapshots, in_c, 
     frequency_points = np.asarray(frequency_points, dtype=np.float64)
     md = ModelDefinition(frequency_points, in_c, csc_array(in_c.shape), in_gamma, in_b, lambda t: 1., lambda t: t, lambda t: t ** 2,
                          lambda t: b_coefficient(t))
+    all_real = impl._real_inputs(in_c, in_gamma, in_b) and not np.iscomplexobj(snapshots)
+    if real_path and not all_real:
+        raise ValueError("real_path=True needs real snapshots and operators")
+    widen = not all_real if real_path is None else not real_path
+    # the snapshot block goes first: the Cholesky-QR passes need nothing else, so the operator uploads (on their own
+    # stream) overlap with them
+    s_dev = dv.real_or_complex_to_device(snapshots, widen=widen)
+    r = s_dev.shape[1]
     if operators_resident:
         key = (id(in_c), id(in_gamma), id(in_b))
         hit = _resident_ops.get(key)
         if hit is None:
             _resident_ops.clear()                                   # one model at a time; the host objects are kept alive so ids stay unique
-            hit = _resident_ops[key] = (impl._DeviceOperators(md), (in_c, in_gamma, in_b))
+            hit = _resident_ops[key] = (impl._DeviceOperators(md, side_stream=True, group_for_r=r), (in_c, in_gamma, in_b))
         ops = hit[0]
     else:
-        ops = impl._DeviceOperators(md)
-    all_real = impl._real_inputs(in_c, in_gamma, in_b) and not np.iscomplexobj(snapshots)
-    if real_path and not all_real:
-        raise ValueError("real_path=True needs real snapshots and operators")
-    widen = not all_real if real_path is None else not real_path
-    _, (a0_r, a1_r, a2_r), b_r, _ = dv.basis_and_projection(dv.real_or_complex_to_device(snapshots, widen=widen), ops.project_block,
-                                                            truncation_tol=impl.TRUNCATION_TOL)
+        ops = impl._DeviceOperators(md, side_stream=True, group_for_r=r)
+    _, (a0_r, a1_r, a2_r), b_r, _ = dv.basis_and_projection(s_dev, ops.project_block, truncation_tol=impl.TRUNCATION_TOL)
     res = impl._sweep_device(frequency_points, [a0_r, a1_r, a2_r], b_r, md.t_a0, md.t_a1, md.t_a2, md.t_b, want_x=False, want_gsm=True)
     gsm = dv.download(res.gsm, pinned_out)
     impl._warn_singular(dv.download(res.info))
