@@ -321,3 +321,22 @@ def test_blocked_cholesky_and_inverse_for_large_r(dv, r):
     bd = dv.to_device_c128(bad)
     dv._potrf_upper(bd, info)
     assert int(info.item()) == (151 if r > 150 else 101)
+
+
+def test_e2e_helper_falls_back_when_choleskyqr2_is_not_enough(dv):
+    """``model_order_reduction_gsm_from_snapshots`` runs the optimistic CholeskyQR2 and verifies its flags with the result
+    download; a nearly collinear snapshot block must take the adaptive (shifted, three-pass) path and still match the oracle."""
+    from morfem_b200 import test_helpers as th
+    nx, ny, nz = 6, 5, 60
+    ct, tt = synthetic.waveguide_operators(nx, ny, nz)
+    n = ct.shape[0]
+    in_c, in_gamma, in_b = synthetic.driver_scaled(ct, tt, synthetic.port_matrix(n, 2, 19))
+    f = synthetic.frequency_points(32)
+    rng = np.random.default_rng(5)
+    base = synthetic.snapshot_matrix(n, 6, seed=2, decay_decades=2.0)
+    snaps = np.hstack([base, base[:, :3] + 1e-9 * rng.standard_normal((n, 3))])        # cond ~ 1e9 after column scaling
+    gsm = th.model_order_reduction_gsm_from_snapshots(f, snaps, in_c, in_gamma, in_b)
+    q_ref, a0, a1, a2, b_r, x_ref, s_ref = orc.hot_path(snaps, f, in_c, csc_array(in_c.shape), in_gamma, in_b)
+    cond = np.array([np.linalg.cond(orc.system_matrix(1.0, t, t ** 2, a0, a1, a2)) for t in f])
+    err = np.linalg.norm((gsm - s_ref).reshape(f.size, -1), axis=1) / np.linalg.norm(s_ref.reshape(f.size, -1), axis=1)
+    assert np.all(err < np.maximum(1e-7, 1e3 * np.finfo(float).eps * cond)), err.max()
