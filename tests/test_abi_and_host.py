@@ -45,6 +45,22 @@ def test_argument_validation_without_gpu():
         _ffi.check(st, "mf_sweep_lu_gsm_c128")
     assert lib.mf_gemm_tn_ws_bytes(64, 64, 100000) >= 64 * 64 * 16
     assert lib.mf_jacobi_svd_ws_bytes(64) > 2 * 64 * 64 * 16
+    # the real float64 twins and the row-grouped SpMM entries validate the same way
+    assert lib.mf_gemm_tn_f64(None, 4, 4, None, 4, 4, 10, None, 4, None, 0, None) == -1 and b"mf_gemm_tn_f64" in lib.mf_last_error()
+    assert lib.mf_gemm_nn_f64(None, 4, 10, 4, None, 4, 4, None, 4, None) == -1
+    assert lib.mf_spmm_csr_f64(None, None, None, 10, None, 4, 4, None, 4, None) == -1
+    assert lib.mf_spmm_group_count(None, None, 10, 4, None, None) == -1
+    assert lib.mf_spmm_grouped_c128(None, None, None, 10, 4, None, 4, 4, None, 4, None) == -1
+    assert lib.mf_sweep_lu_gsm_f64(None, None, None, 8, None, 2, 8, 2, None, None, None, None, None, 4, None, None, None, None) == -1
+    assert lib.mf_jacobi_svd_f64(None, 4, 4, None, 4, None, 10, 1e-15, None, None) == -1
+    assert lib.mf_gemm_tn_f64_ws_bytes(64, 64, 100000) >= 64 * 64 * 8
+    # shape support queries (host only): which kernel family serves which (r, m)
+    assert lib.mf_spmm_group_size(64) == 4 and lib.mf_spmm_group_size(256) == 2
+    assert lib.mf_sweep_f64_supported(64, 2) == 1 and lib.mf_sweep_f64_supported(256, 4) == 0
+    assert lib.mf_jacobi_svd_f64_supported(64) == 1 and lib.mf_jacobi_svd_f64_supported(65) == 0
+    assert all(lib.mf_sweep_variant_supported(r, 4, 3) == 1 for r in (1, 64, 112, 113, 256, 512))
+    assert lib.mf_sweep_variant_supported(600, 4, 3) == 0 and lib.mf_sweep_variant_supported(600, 4, 1) == 1
+    assert lib.mf_sweep_ws_bytes(256, 4, 1000, 0) >= 148 * 256 * 264 * 16 and lib.mf_sweep_ws_bytes(64, 2, 1000, 0) == 256
 
 
 def test_product_path_refuses_to_run_without_cuda():
@@ -55,6 +71,25 @@ def test_product_path_refuses_to_run_without_cuda():
     md = impl.ModelDefinition(np.linspace(3e9, 5e9, 4), a0, a1, a2, b, lambda t: 1.0, lambda t: t, lambda t: t ** 2, th.b_coefficient)
     with pytest.raises(_ffi.MorfemB200Error):
         impl.solve_finite_element_method(md)      # no CPU fallback on the hot path
+
+
+def test_b_coefficient_scalar_and_array_forms_agree():
+    """test_helpers.py:70-72: scalar form identical to the reference's formula (math.sqrt, ValueError below cutoff); the array
+    form agrees to 1 ulp and raises for a point below the cutoff like the scalar loop would."""
+    import math
+    from scipy.constants import pi, c
+    f = np.linspace(3e9, 5e9, 2001)
+    ref = np.array([math.sqrt(math.sqrt(((2 * pi * t) / c) ** 2 - 54.5976295582387 ** 2) / t) for t in f])
+    assert np.array_equal(np.array([th.b_coefficient(float(t)) for t in f]), ref)
+    vec = th.b_coefficient(f)
+    assert np.max(np.abs(vec - ref) / ref) <= 2 * np.finfo(float).eps
+    assert np.max(np.abs(impl.coefficient_array(th.b_coefficient, f) - ref) / ref) <= 2 * np.finfo(float).eps
+    with pytest.raises(ValueError):
+        th.b_coefficient(1e9)
+    with pytest.raises(ValueError):
+        th.b_coefficient(np.array([4e9, 1e9]))
+    with pytest.raises(ValueError):
+        impl.coefficient_array(th.b_coefficient, np.array([4e9, 1e9]))
 
 
 def test_coefficient_array_vectorised_and_scalar_fallback():
