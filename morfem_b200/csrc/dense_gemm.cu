@@ -23,13 +23,14 @@ constexpr int TN_STAGE_ELEMS = KC * (TN_LDA + TN_LDB);
 
 __global__ void __launch_bounds__(TN_THREADS, 2)
 gemm_tn_kernel(const cplx* __restrict__ A, long long lda, int ra, const cplx* __restrict__ B, long long ldb, int rb,
-               long long n, long long rows_per_split, int conj_a, cplx* __restrict__ part) {
+               long long n, long long rows_per_split, int conj_a, cplx* __restrict__ part, int herm) {
     extern __shared__ __align__(16) cplx smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
     const int wi = warp >> 1, wj = warp & 1;
     const int ntj = (rb + TN_TJ - 1) / TN_TJ;
     const int ti = blockIdx.x / ntj, tj = blockIdx.x - ti * ntj;
+    if (herm && ti > tj) return;               // Gram matrix A^H A: the lower tiles are the conjugate transposes of the upper ones
     const int i0 = ti * TN_TI, j0 = tj * TN_TJ;
     const long long n0 = (long long)blockIdx.y * rows_per_split;
     long long n1 = n0 + rows_per_split; if (n1 > n) n1 = n;
@@ -112,11 +113,17 @@ gemm_tn_kernel(const cplx* __restrict__ A, long long lda, int ra, const cplx* __
 // splits w, w+8, ... with independent loads in flight; the eight warp partials are combined in warp order.
 constexpr int RED_WARPS = 8;
 __global__ void __launch_bounds__(RED_WARPS * 32)
-reduce_partials_kernel(const cplx* __restrict__ part, int nsplit, int ra, int rb, cplx* __restrict__ C, long long ldc) {
+reduce_partials_kernel(const cplx* __restrict__ part, int nsplit, int ra, int rb, cplx* __restrict__ C, long long ldc, int herm) {
     __shared__ cplx red[RED_WARPS][32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long long total = (long long)ra * rb;
-    const long long idx = (long long)blockIdx.x * 32 + lane;
+    const long long oidx = (long long)blockIdx.x * 32 + lane;
+    long long idx = oidx;
+    bool mirror = false;
+    if (herm && oidx < total) {                // lower tiles were not computed: read the mirrored element and conjugate
+        const int i = (int)(oidx / rb), j = (int)(oidx - (long long)i * rb);
+        if (i / TN_TI > j / TN_TJ) { idx = (long long)j * rb + i; mirror = true; }
+    }
     cplx acc0 = cmake(0.0, 0.0), acc1 = cmake(0.0, 0.0);
     if (idx < total) {
         int s = warp;
@@ -128,21 +135,25 @@ reduce_partials_kernel(const cplx* __restrict__ part, int nsplit, int ra, int rb
     }
     red[warp][lane] = cadd(acc0, acc1);
     __syncthreads();
-    if (warp == 0 && idx < total) {
+    if (warp == 0 && oidx < total) {
         cplx acc = red[0][lane];
 #pragma unroll
         for (int w = 1; w < RED_WARPS; ++w) acc = cadd(acc, red[w][lane]);
-        const int i = (int)(idx / rb), j = (int)(idx - (long long)i * rb);
+        if (mirror) acc.y = -acc.y;
+        const int i = (int)(oidx / rb), j = (int)(oidx - (long long)i * rb);
         C[i * ldc + j] = acc;
     }
 }
 
-void tn_plan(int ra, int rb, long long n, int& tiles, int& nsplit, long long& rows_per_split) {
+// `symm`: only the upper-triangular tiles do work (Gram matrices), so the row index is split into more, shorter ranges
+void tn_plan(int ra, int rb, long long n, int& tiles, int& nsplit, long long& rows_per_split, bool symm = false) {
     tiles = ((ra + TN_TI - 1) / TN_TI) * ((rb + TN_TJ - 1) / TN_TJ);
+    const int nt = (ra + TN_TI - 1) / TN_TI;
+    const int work_tiles = symm ? nt * (nt + 1) / 2 : tiles;
     const int target = 148 * 2 * 2;   // two waves of two resident CTAs per SM (B200: 148 SMs)
     long long max_split = (n + (long long)KC * 8 - 1) / ((long long)KC * 8);
     if (max_split < 1) max_split = 1;
-    long long s = target / tiles; if (s < 1) s = 1; if (s > max_split) s = max_split;
+    long long s = target / work_tiles; if (s < 1) s = 1; if (s > max_split) s = max_split;
     rows_per_split = (n + s - 1) / s;
     rows_per_split = (rows_per_split + KC - 1) / KC * KC;
     if (rows_per_split < KC) rows_per_split = KC;
@@ -245,9 +256,10 @@ gemm_nn_kernel(const cplx* __restrict__ A, long long lda, long long n, int ra, c
 
 extern "C" size_t mf_gemm_tn_ws_bytes(int ra, int rb, int64_t n) {
     if (ra <= 0 || rb <= 0 || n <= 0) return 16;
-    int tiles, nsplit; long long rps;
+    int tiles, nsplit, nsplit2 = 0; long long rps;
     tn_plan(ra, rb, n, tiles, nsplit, rps);
-    return sizeof(cplx) * (size_t)nsplit * ra * rb;
+    if (ra == rb) tn_plan(ra, rb, n, tiles, nsplit2, rps, true);       // the Gram path uses more splits
+    return sizeof(cplx) * (size_t)(nsplit > nsplit2 ? nsplit : nsplit2) * ra * rb;
 }
 
 extern "C" int mf_gemm_tn_c128(const mf_c128* A, int64_t lda, int ra, const mf_c128* B, int64_t ldb, int rb, int64_t n,
@@ -261,14 +273,15 @@ extern "C" int mf_gemm_tn_c128(const mf_c128* A, int64_t lda, int ra, const mf_c
     if (!ws || ws_bytes < mf_gemm_tn_ws_bytes(ra, rb, n)) MF_FAIL_ARG(11, "workspace too small (mf_gemm_tn_ws_bytes)");
     cudaStream_t st = (cudaStream_t)stream;
     int tiles, nsplit; long long rps;
-    tn_plan(ra, rb, n > 0 ? n : 1, tiles, nsplit, rps);
+    const int herm = (conj_a && (const void*)A == (const void*)B && lda == ldb && ra == rb) ? 1 : 0;
+    tn_plan(ra, rb, n > 0 ? n : 1, tiles, nsplit, rps, herm != 0);
     const size_t smem = sizeof(cplx) * STAGES * TN_STAGE_ELEMS;
     MF_CHECK_CUDA(cudaFuncSetAttribute(gemm_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(tiles, nsplit);
-    gemm_tn_kernel<<<grid, TN_THREADS, smem, st>>>((const cplx*)A, lda, ra, (const cplx*)B, ldb, rb, n, rps, conj_a, (cplx*)ws);
+    gemm_tn_kernel<<<grid, TN_THREADS, smem, st>>>((const cplx*)A, lda, ra, (const cplx*)B, ldb, rb, n, rps, conj_a, (cplx*)ws, herm);
     MF_CHECK_LAUNCH();
     long long total = (long long)ra * rb;
-    reduce_partials_kernel<<<(unsigned)((total + 31) / 32), RED_WARPS * 32, 0, st>>>((const cplx*)ws, nsplit, ra, rb, (cplx*)C, ldc);
+    reduce_partials_kernel<<<(unsigned)((total + 31) / 32), RED_WARPS * 32, 0, st>>>((const cplx*)ws, nsplit, ra, rb, (cplx*)C, ldc, herm);
     MF_CHECK_LAUNCH();
     return 0;
 }

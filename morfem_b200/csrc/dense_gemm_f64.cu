@@ -27,13 +27,14 @@ __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src, 
 
 __global__ void __launch_bounds__(TN_THREADS, 2)
 gemm_tn_f64_kernel(const double* __restrict__ A, long long lda, int ra, const double* __restrict__ B, long long ldb, int rb,
-                   long long n, long long rows_per_split, double* __restrict__ part, int vec_ok) {
+                   long long n, long long rows_per_split, double* __restrict__ part, int vec_ok, int symm) {
     extern __shared__ __align__(16) double smem_d[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
     const int wi = warp >> 1, wj = warp & 1;
     const int ntj = (rb + TN_TJ - 1) / TN_TJ;
     const int ti = blockIdx.x / ntj, tj = blockIdx.x - ti * ntj;
+    if (symm && ti > tj) return;               // Gram matrix A^T A: the lower tiles mirror the upper ones
     const int i0 = ti * TN_TI, j0 = tj * TN_TJ;
     const long long n0 = (long long)blockIdx.y * rows_per_split;
     long long n1 = n0 + rows_per_split; if (n1 > n) n1 = n;
@@ -123,11 +124,16 @@ gemm_tn_f64_kernel(const double* __restrict__ A, long long lda, int ra, const do
 
 constexpr int RED_WARPS = 8;
 __global__ void __launch_bounds__(RED_WARPS * 32)
-reduce_partials_f64_kernel(const double* __restrict__ part, int nsplit, int ra, int rb, double* __restrict__ C, long long ldc) {
+reduce_partials_f64_kernel(const double* __restrict__ part, int nsplit, int ra, int rb, double* __restrict__ C, long long ldc, int symm) {
     __shared__ double red[RED_WARPS][32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long long total = (long long)ra * rb;
-    const long long idx = (long long)blockIdx.x * 32 + lane;
+    const long long oidx = (long long)blockIdx.x * 32 + lane;
+    long long idx = oidx;
+    if (symm && oidx < total) {
+        const int i = (int)(oidx / rb), j = (int)(oidx - (long long)i * rb);
+        if (i / TN_TI > j / TN_TJ) idx = (long long)j * rb + i;
+    }
     double acc0 = 0.0, acc1 = 0.0;
     if (idx < total) {
         int s = warp;
@@ -136,21 +142,24 @@ reduce_partials_f64_kernel(const double* __restrict__ part, int nsplit, int ra, 
     }
     red[warp][lane] = acc0 + acc1;
     __syncthreads();
-    if (warp == 0 && idx < total) {
+    if (warp == 0 && oidx < total) {
         double acc = red[0][lane];
 #pragma unroll
         for (int w = 1; w < RED_WARPS; ++w) acc += red[w][lane];
-        const int i = (int)(idx / rb), j = (int)(idx - (long long)i * rb);
+        const int i = (int)(oidx / rb), j = (int)(oidx - (long long)i * rb);
         C[i * ldc + j] = acc;
     }
 }
 
-void tn_plan(int ra, int rb, long long n, int& tiles, int& nsplit, long long& rows_per_split) {
+// `symm`: only the upper-triangular tiles do work (Gram matrices), so the row index is split into more, shorter ranges
+void tn_plan(int ra, int rb, long long n, int& tiles, int& nsplit, long long& rows_per_split, bool symm = false) {
     tiles = ((ra + TN_TI - 1) / TN_TI) * ((rb + TN_TJ - 1) / TN_TJ);
+    const int nt = (ra + TN_TI - 1) / TN_TI;
+    const int work_tiles = symm ? nt * (nt + 1) / 2 : tiles;
     const int target = 148 * 2 * 2;
     long long max_split = (n + (long long)KC * 8 - 1) / ((long long)KC * 8);
     if (max_split < 1) max_split = 1;
-    long long s = target / tiles; if (s < 1) s = 1; if (s > max_split) s = max_split;
+    long long s = target / work_tiles; if (s < 1) s = 1; if (s > max_split) s = max_split;
     rows_per_split = (n + s - 1) / s;
     rows_per_split = (rows_per_split + KC - 1) / KC * KC;
     if (rows_per_split < KC) rows_per_split = KC;
@@ -240,9 +249,10 @@ gemm_nn_f64_kernel(const double* __restrict__ A, long long lda, long long n, int
 
 extern "C" size_t mf_gemm_tn_f64_ws_bytes(int ra, int rb, int64_t n) {
     if (ra <= 0 || rb <= 0 || n <= 0) return 16;
-    int tiles, nsplit; long long rps;
+    int tiles, nsplit, nsplit2 = 0; long long rps;
     tn_plan(ra, rb, n, tiles, nsplit, rps);
-    return sizeof(double) * (size_t)nsplit * ra * rb;
+    if (ra == rb) tn_plan(ra, rb, n, tiles, nsplit2, rps, true);
+    return sizeof(double) * (size_t)(nsplit > nsplit2 ? nsplit : nsplit2) * ra * rb;
 }
 
 extern "C" int mf_gemm_tn_f64(const double* A, int64_t lda, int ra, const double* B, int64_t ldb, int rb, int64_t n,
@@ -256,16 +266,17 @@ extern "C" int mf_gemm_tn_f64(const double* A, int64_t lda, int ra, const double
     if (!ws || ws_bytes < mf_gemm_tn_f64_ws_bytes(ra, rb, n)) MF_FAIL_ARG(10, "workspace too small (mf_gemm_tn_f64_ws_bytes)");
     cudaStream_t st = (cudaStream_t)stream;
     int tiles, nsplit; long long rps;
-    tn_plan(ra, rb, n > 0 ? n : 1, tiles, nsplit, rps);
+    const int symm = (A == B && lda == ldb && ra == rb) ? 1 : 0;
+    tn_plan(ra, rb, n > 0 ? n : 1, tiles, nsplit, rps, symm != 0);
     const size_t smem = sizeof(double) * STAGES * TN_STAGE_ELEMS;
     MF_CHECK_CUDA(cudaFuncSetAttribute(gemm_tn_f64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int vec_ok = ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B)) & 15) == 0 && (lda % 2) == 0 && (ldb % 2) == 0 &&
                        (ra % 2) == 0 && (rb % 2) == 0;
     dim3 grid(tiles, nsplit);
-    gemm_tn_f64_kernel<<<grid, TN_THREADS, smem, st>>>(A, lda, ra, B, ldb, rb, n, rps, (double*)ws, vec_ok);
+    gemm_tn_f64_kernel<<<grid, TN_THREADS, smem, st>>>(A, lda, ra, B, ldb, rb, n, rps, (double*)ws, vec_ok, symm);
     MF_CHECK_LAUNCH();
     const long long total = (long long)ra * rb;
-    reduce_partials_f64_kernel<<<(unsigned)((total + 31) / 32), RED_WARPS * 32, 0, st>>>((const double*)ws, nsplit, ra, rb, C, ldc);
+    reduce_partials_f64_kernel<<<(unsigned)((total + 31) / 32), RED_WARPS * 32, 0, st>>>((const double*)ws, nsplit, ra, rb, C, ldc, symm);
     MF_CHECK_LAUNCH();
     return 0;
 }

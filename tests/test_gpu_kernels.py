@@ -252,3 +252,21 @@ def test_real_jacobi_svd_twin(dv, r):
     gram = t @ t.T
     assert np.max(np.abs(gram - np.diag(np.diag(gram)))) < 1e-12 * s_ref[0] ** 2
     assert 0 < int(sweeps.item()) < 40
+
+
+@pytest.mark.parametrize("n,r", [(5000, 64), (3000, 130), (2500, 256), (700, 300)])
+def test_gram_matrices_use_the_symmetric_tile_path(dv, n, r):
+    """gemm_tn(a, a, conj=True) computes only the upper 64 x 64 tiles and mirrors the rest: result exactly Hermitian."""
+    rng = np.random.default_rng(n)
+    a = crandn(rng, n, r)
+    ad = dv.to_device_c128(a)
+    g = dv.gemm_tn(ad, ad, conj=True).cpu().numpy()
+    assert rel(g, a.conj().T @ a) < 1e-13
+    lower_tiles = (np.arange(r)[:, None] // 64) > (np.arange(r)[None, :] // 64)
+    assert np.array_equal(g[lower_tiles], g.conj().T[lower_tiles])
+    ar = torch.from_numpy(np.ascontiguousarray(a.real)).cuda()
+    gr = dv.gemm_tn(ar, ar).cpu().numpy()
+    assert rel(gr, a.real.T @ a.real) < 1e-13 and np.array_equal(gr[lower_tiles], gr.T[lower_tiles])
+    # a plain transpose of the same operand (conj=False, complex) is NOT Hermitian and must take the general path
+    gt = dv.gemm_tn(ad, ad, conj=False).cpu().numpy()
+    assert rel(gt, a.T @ a) < 1e-13
