@@ -227,12 +227,14 @@ def solve_finite_element_method(md: ModelDefinition):
             x_in_domain[i] = solve_fem_point(domain[i], md)
         return x_in_domain
     from . import device as dv
-    ops = [None if _is_zero_operator(a) else dv.to_device_c128(a) for a in (md.a0, md.a1, md.a2)]
-    b_r = dv.to_device_c128(md.b)
+    real = _real_inputs(md.a0, md.a1, md.a2, md.b)        # the reference's reduced models are real: float64 sweep kernel
+    up = (lambda a: dv.real_or_complex_to_device(np.asarray(a))) if real else dv.to_device_c128
+    ops = [None if _is_zero_operator(a) else up(a) for a in (md.a0, md.a1, md.a2)]
+    b_r = up(md.b)
     res = _sweep_device(domain, ops, b_r, md.t_a0, md.t_a1, md.t_a2, md.t_b, want_x=True, want_gsm=False)
     x = res.x.cpu().numpy()
     _warn_singular(res.info.cpu().numpy())
-    return np.ascontiguousarray(x.real) if _real_inputs(md.a0, md.a1, md.a2, md.b) else x
+    return np.ascontiguousarray(x.real) if real else x
 
 
 def _orthonormal_basis_device(snapshots: np.ndarray):

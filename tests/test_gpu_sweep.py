@@ -243,3 +243,28 @@ def test_real_sweep_reports_singular_points(dv):
     a0[11, 11] = 0.0
     res = run_sweep_real(dv, np.array([3e9, 4e9]), a0, None, None, np.ones((r, m)), np.ones(2), want_gsm=False)
     assert list(res.info.cpu().numpy()) == [12, 12]
+
+
+def test_public_stage3_and_stage4_api_match_live_reference(dv):
+    """The reference-facing calls themselves: ``solve_finite_element_method`` / ``solve_fem_point`` (implementation.py:189-194,
+    :468-480) on a dense reduced ModelDefinition and ``generalized_scattering_matrix`` (test_helpers.py:9-14), against the
+    committed outputs of the live reference; real input -> float64 result like the reference (:190)."""
+    from morfem_b200 import implementation as impl, test_helpers as th
+    g = np.load(os.path.join(GOLDEN, "reduced_r33_m3.npz"))
+    f = g["f"]
+    md = impl.ModelDefinition(f, g["a0"], g["a1"], g["a2"], g["b"], lambda t: 1.0, lambda t: t, lambda t: t ** 2, th.b_coefficient)
+    x = impl.solve_finite_element_method(md)
+    assert x.dtype == np.float64 and x.shape == g["x"].shape and x.flags.c_contiguous
+    tol = np.maximum(1e-10, 20 * EPS * g["cond"])
+    assert np.all(per_point_rel(x, g["x"]) < tol)
+    i = f.size // 2
+    xi = impl.solve_fem_point(f[i], md)
+    assert xi.shape == g["x"][i].shape and np.linalg.norm(xi - g["x"][i]) / np.linalg.norm(g["x"][i]) < tol[i]
+    s_i = th.generalized_scattering_matrix(f[i], g["x"][i], th.b_coefficient(f[i]) * g["b"])
+    assert np.linalg.norm(s_i - g["gsm"][i]) / np.linalg.norm(g["gsm"][i]) < tol[i]
+    # complex operands: complex result (documented deviation D2), checked against the oracle's restatement
+    a0c = g["a0"] * (1.0 + 0.01j)
+    mdc = impl.ModelDefinition(f[:5], a0c, g["a1"], g["a2"], g["b"], lambda t: 1.0, lambda t: t, lambda t: t ** 2, th.b_coefficient)
+    xc = impl.solve_finite_element_method(mdc)
+    xr = orc.reduced_sweep(f[:5], a0c, g["a1"], g["a2"], g["b"], lambda t: 1.0, lambda t: t, lambda t: t ** 2, orc.b_coefficient, complex_ok=True)
+    assert np.iscomplexobj(xc) and np.all(per_point_rel(xc, xr) < 1e-8)
