@@ -237,9 +237,17 @@ def solve_finite_element_method(md: ModelDefinition):
     return np.ascontiguousarray(x.real) if real else x
 
 
-def _orthonormal_basis_device(snapshots: np.ndarray):
+def _block_to_device(arr, md: ModelDefinition):
+    """Tall host block -> device in the model's field: float64 for real models (the real twins of the kernels run, like
+    the reference's own float64 arithmetic), complex128 otherwise."""
     from . import device as dv
-    s = dv.to_device_c128(snapshots)
+    real = _real_inputs(md.a0, md.a1, md.a2, md.b) and not np.iscomplexobj(arr)
+    return dv.real_or_complex_to_device(np.asarray(arr), widen=not real)
+
+
+def _orthonormal_basis_device(snapshots: np.ndarray, md: Optional[ModelDefinition] = None):
+    from . import device as dv
+    s = dv.to_device_c128(snapshots) if md is None else _block_to_device(snapshots, md)
     q, info = dv.orthonormalize(s, truncation_tol=TRUNCATION_TOL)
     return q, info
 
@@ -252,7 +260,7 @@ def projection_base_equally_distributed(md: ModelDefinition):
     q = np.empty((md.b.shape[0], vector_count * reduction_indices.size))
     for i in range(reduction_indices.size):
         q[:, vector_count * i:vector_count * i + vector_count] = solve_fem_point(md.domain[reduction_indices[i]], md)
-    qd, _ = _orthonormal_basis_device(q)
+    qd, _ = _orthonormal_basis_device(q, md)
     return _basis_to_host(qd, md)
 
 
@@ -269,10 +277,11 @@ def error_estimator(md: ModelDefinition, q, opm=None, time_stats=None, _ops: Opt
     from . import device as dv
     import torch
     ops = _ops or _DeviceOperators(md)
-    qd = q if isinstance(q, torch.Tensor) else dv.to_device_c128(q)
+    qd = q if isinstance(q, torch.Tensor) else _block_to_device(q, md)
+    c128 = lambda t: t if (t is None or t.is_complex()) else t.to(torch.complex128)      # noqa: E731  (r x r blocks for the estimator kernel)
     ys = [None if ops.zero[i] else dv.spmm(ops.a_csr(i), qd) for i in range(3)]
-    g = [[None if (ys[a] is None or ys[b] is None) else dv.gemm_tn(ys[a], ys[b], conj=True) for b in range(3)] for a in range(3)]
-    hb = [None if y is None else dv.project_rhs(ops.b, y, 0, conj=True) for y in ys]
+    g = [[None if (ys[a] is None or ys[b] is None) else c128(dv.gemm_tn(ys[a], ys[b], conj=True)) for b in range(3)] for a in range(3)]
+    hb = [None if y is None else c128(dv.project_rhs(ops.b, y, 0, conj=True)) for y in ys]
     bb = dv.to_device_c128((h(ops.b_host) @ ops.b_host).toarray())
     a0_r, a1_r, a2_r, b_r = ops.project(qd)
     res = _sweep_device(md.domain, [a0_r, a1_r, a2_r], b_r, md.t_a0, md.t_a1, md.t_a2, md.t_b, want_x=True, want_gsm=False)
@@ -298,13 +307,16 @@ def projection_base(md: ModelDefinition, _return_device: bool = False):
     from . import device as dv
     ops = _DeviceOperators(md)
     initial_vectors = np.hstack((solve_fem_point(md.domain[0], md), solve_fem_point(md.domain[-1], md)))
-    qd, _ = _orthonormal_basis_device(initial_vectors)
+    qd, _ = _orthonormal_basis_device(initial_vectors, md)
     while True:
         q_new, _error = new_solution_for_projection_base(md, qd, _ops=ops)
         if q_new is None:
             break
         import torch
-        stacked = torch.cat((qd, dv.to_device_c128(q_new)), dim=1).contiguous()
+        new = _block_to_device(q_new, md)
+        if new.dtype != qd.dtype:                 # a complex full-order solution joins a real basis: continue in complex128
+            qd, new = qd.to(torch.complex128), new.to(torch.complex128)
+        stacked = torch.cat((qd, new), dim=1).contiguous()
         qd, _ = dv.orthonormalize(stacked, truncation_tol=TRUNCATION_TOL)
     return qd if _return_device else _basis_to_host(qd, md)
 
@@ -352,7 +364,7 @@ def morfem(domain: np.ndarray, a0: csc_array, a1: csc_array, a2: csc_array, b: c
     md = ModelDefinition(domain, a0, a1, a2, b, t_a0, t_a1, t_a2, t_b)
     start = time.time()
     if USE_EQUALLY_DISTRIBUTED:
-        qd = dv.to_device_c128(projection_base_equally_distributed(md))
+        qd = _block_to_device(projection_base_equally_distributed(md), md)
     else:
         qd = projection_base(md, _return_device=True)
     if VERBOSE:

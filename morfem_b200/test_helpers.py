@@ -103,7 +103,7 @@ def finite_element_method_model_order_reduction_gsm(frequency_points, gate_count
                          lambda t: b_coefficient(t))
     start = time.time()
     if impl.USE_EQUALLY_DISTRIBUTED:
-        qd = dv.to_device_c128(impl.projection_base_equally_distributed(md))
+        qd = impl._block_to_device(impl.projection_base_equally_distributed(md), md)
     else:
         qd = impl.projection_base(md, _return_device=True)
     ops = impl._DeviceOperators(md)
