@@ -1,28 +1,38 @@
-// Blocked sweep for large reduced models (113 <= r <= 512): one CTA (8 warps) per frequency point, augmented matrix
-// [A(t) | cb(t) Br] in a per-CTA slot of a global workspace that stays L2 resident, two-level blocked right-looking LU.
+// Blocked sweep for large reduced models (113 <= r <= 512): one CTA per frequency point (several CTAs per SM, see
+// stream_geom), augmented matrix [A(t) | cb(t) Br] in a per-CTA slot of a global workspace, two-level blocked
+// right-looking LU.
 //
-// Outer step (NBO = 32 columns, 16 for r > 256):
+// Outer step (NBO = 16 columns; 32 in the one-CTA-per-SM geometry):
 //   1. the (R - col0) x NBO outer panel is copied into shared memory (same XOR-swizzled layout as sweep_blocked.cu);
 //   2. it is factored there in inner panels of 8 columns: ALL warps take part in the pivot search (rows split over the
 //      CTA, one CTA barrier per column, candidates exchanged through shared memory), then the row exchanges, the
 //      triangular solve and the DMMA update of the rest of the outer panel, exactly as in sweep_blocked.cu;
 //   3. the composite row permutation of the NBO exchanges is formed once and applied to the trailing columns as a
 //      gather (all loads before all stores) instead of NBO dependent row swaps through L2;
-//   4. per chunk of 64 trailing columns: U12 = L11^-1 A12 by a blocked forward substitution (DMMA + 8 x 8 in-block
+//   4. per chunk of ST_CW trailing columns: U12 = L11^-1 A12 by a blocked forward substitution (DMMA + 8 x 8 in-block
 //      solves) in shared memory, written back as final U rows, then A22 -= L21 U12 with the C tiles streamed
-//      global -> registers -> global, A fragments from the shared outer panel, B fragments from the shared U12 chunk
-//      (32 DMMAs per 8 x 8 tile per pair of 16-byte global accesses: FP64-pipe bound, not L2 bound).
-// Traffic per point at r = 256: ~6 MB through L2 for 47.9 MFLOP; the FP64 pipe is the roofline.
+//      global -> registers -> global, A fragments from the shared outer panel, B fragments from the shared U12 chunk.
+// FUSE: there is no assembly pass.  The FIRST outer step reads its operands straight from the L2-resident reduced
+// operators (aug(i, j) = c0 A0 + c1 A1 + c2 A2 | cb Br): the panel load, the rows that land in U12 and the C tiles
+// of the first trailing update (row idx[x] of the operators = the row the exchanges brought to position x), so the
+// matrix is written to its slot once, already updated (saves one write + one read of the slot per point).
+// Traffic per point at r = 256: ~6 MB (NBO = 32) / ~11 MB (NBO = 16) for 47.9 MFLOP.
 // Back substitution is row oriented (coalesced rows of U from L2, solution in shared memory); the impedance matrix
 // goes to S and gsm_finish_kernel completes the S-parameter algebra (test_helpers.py:11-14).
 // Reference semantics: implementation.py:468-480, :526-533 (lu_factor / lu_solve of the symmetrised system matrix).
+#include <stdlib.h>
 #include "sweep_blocked.cuh"
 
 namespace {
 
-constexpr int ST_NW = 8, ST_NT = ST_NW * 32;
-constexpr int ST_CW = 64;                    // trailing columns per chunk
 constexpr int ST_MAXMOVED = 64;              // rows touched by the composite permutation of one outer panel (<= 2 NBO)
+constexpr int ST_MAXNW = 8;
+#ifndef MF_STREAM_SMALL_R
+#define MF_STREAM_SMALL_R 128
+#endif
+#ifndef MF_STREAM_DEFAULT_FUSE
+#define MF_STREAM_DEFAULT_FUSE true
+#endif                  // most warps per CTA of any geometry (sizes the candidate exchange)
 
 struct CandKey { double v; int pos; int pad; };
 
@@ -32,9 +42,10 @@ struct CandKey { double v; int pos; int pad; };
 // (magnitude, position, finished row with the reciprocal pivot) to shared memory, ONE CTA barrier, every thread
 // picks the same global winner from the NW candidates.  Multipliers are stored negated.  pvl[j] = position (local
 // row of PB) the j-th pivot row came from.  Ends with all rows written back; the caller synchronises.
-template <int SL>
+template <int SL, int ST_NW>
 __device__ __forceinline__ void panel_factor_mw(cplx* PB, const int LDp, const int rows, const int row0, const int tid,
                                                 CandKey* candk, cplx* candrow, int* pvl, int* info_sh, const int info_base) {
+    constexpr int ST_NT = ST_NW * 32;
     const int lane = tid & 31, warp = tid >> 5;
     cplx a[SL][8];
     int pos[SL];
@@ -74,8 +85,8 @@ __device__ __forceinline__ void panel_factor_mw(cplx* PB, const int LDp, const i
                 own = own && (pbest == pmin);
             }
         }
-        CandKey* ck = candk + (j & 1) * ST_NW;
-        cplx* cr = candrow + (j & 1) * ST_NW * 8;
+        CandKey* ck = candk + (j & 1) * ST_MAXNW;
+        cplx* cr = candrow + (j & 1) * ST_MAXNW * 8;
         if (own) {                                   // this warp's candidate: key and finished row
             ck[warp].v = vb; ck[warp].pos = pbest;
 #pragma unroll
@@ -157,10 +168,13 @@ __device__ __forceinline__ FragOff make_fragoff(int lane, int LD) {
 }
 
 // ---- the kernel ---------------------------------------------------------------------------------------------------
-// NBO = outer panel width (32 or 16), SL = rows per thread in the inner panel factorisation (R <= 256 SL).
-template <int NBO, int SL>
-__global__ void __launch_bounds__(ST_NT, 1) sweep_stream_kernel(SweepParams p, int R, int LD) {
+// NBO = outer panel width (32 or 16), ST_NW = warps per CTA, ST_CW = trailing columns per chunk, RMAX = largest padded
+// size the instance handles (sizes the per-thread register arrays), MINB = CTAs per SM the register budget is set for.
+template <int NBO, int ST_NW, int ST_CW, int RMAX, int MINB, bool FUSE>
+__global__ void __launch_bounds__(ST_NW * 32, MINB) sweep_stream_kernel(SweepParams p, int R, int LD) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int ST_NT = ST_NW * 32;
+    constexpr int SL = RMAX / ST_NT;                             // rows per thread in the inner panel factorisation
     constexpr int NCBP = NBO / 8;
     const int r = p.r, m = p.m, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3, sg = swz(g);
@@ -168,8 +182,8 @@ __global__ void __launch_bounds__(ST_NT, 1) sweep_stream_kernel(SweepParams p, i
     cplx* PB = reinterpret_cast<cplx*>(smem_raw);                 // R x NBO outer panel (later: the solution, R x m)
     cplx* UB = PB + (size_t)R * NBO;                              // NBO x ST_CW chunk of U12
     cplx* candrow = UB + NBO * ST_CW;                             // 2 x NW x 8
-    CandKey* candk = reinterpret_cast<CandKey*>(candrow + 2 * ST_NW * 8);   // 2 x NW
-    int* idx = reinterpret_cast<int*>(candk + 2 * ST_NW);         // R: composite permutation
+    CandKey* candk = reinterpret_cast<CandKey*>(candrow + 2 * ST_MAXNW * 8);   // 2 x NW
+    int* idx = reinterpret_cast<int*>(candk + 2 * ST_MAXNW);         // R: composite permutation
     int* mv_dst = idx + R;                                        // ST_MAXMOVED
     int* mv_src = mv_dst + ST_MAXMOVED;                           // ST_MAXMOVED
     int* lp = mv_src + ST_MAXMOVED;                               // NBO local pivot positions of the outer panel
@@ -183,8 +197,26 @@ __global__ void __launch_bounds__(ST_NT, 1) sweep_stream_kernel(SweepParams p, i
     for (long long pt = blockIdx.x; pt < p.F; pt += gridDim.x) {
         const double c0 = p.c0[pt], c1 = p.c1[pt], c2 = p.c2[pt], cb = p.cb[pt];
         // ---- assemble [A(t) | cb Br] into the slot, identity on the padded diagonal ----
-        constexpr int RPLA = (NBO == 32) ? 8 : 16;                // row elements per lane (R <= 32 RPLA)
-        constexpr int RGA = (NBO == 32) ? 2 : 1;                  // operator rows per warp iteration (all their loads in flight)
+        // FUSE: no assembly pass -- the first outer step reads its operands straight from the operators (aug below)
+        constexpr int RPLA = RMAX / 32;                           // row elements per lane (R <= 32 RPLA)
+        constexpr int RGA = (RMAX <= 256 && MINB == 1) ? 2 : 1;   // operator rows per warp iteration (all their loads in flight)
+        // element (i, j) of the augmented matrix [A(t) | cb Br], identity on the padded diagonal
+        auto aug = [&](const int i, const int j) -> cplx {
+            cplx v = cmake(0.0, 0.0);
+            if (j < R) {
+                if (i < r && j < r) {
+                    const long long off = (long long)i * p.lda + j;
+                    if (hasA0) { const cplx x = __ldg(p.A0 + off); v.x = c0 * x.x; v.y = c0 * x.y; }
+                    if (hasA1) { const cplx x = __ldg(p.A1 + off); v.x = fma(c1, x.x, v.x); v.y = fma(c1, x.y, v.y); }
+                    if (hasA2) { const cplx x = __ldg(p.A2 + off); v.x = fma(c2, x.x, v.x); v.y = fma(c2, x.y, v.y); }
+                } else if (i == j) v.x = 1.0;
+            } else if (i < r && j - R < m) {
+                const cplx x = __ldg(p.Br + (long long)i * p.ldb + (j - R));
+                v.x = cb * x.x; v.y = cb * x.y;
+            }
+            return v;
+        };
+        if (!FUSE)
         for (int i0 = warp * RGA; i0 < R; i0 += ST_NW * RGA) {
             cplx v[RGA][RPLA];
 #pragma unroll
@@ -224,6 +256,21 @@ __global__ void __launch_bounds__(ST_NT, 1) sweep_stream_kernel(SweepParams p, i
         for (int col0 = 0; col0 < R; col0 += NBO) {
             const int rows = R - col0;                           // rows (and local row count) of the outer panel
             // 1. outer panel -> shared memory
+            const bool first = FUSE && col0 == 0;
+            if (first) {                                         // 32 / NBO rows per warp instruction, four of those in flight
+                constexpr int RW = 32 / NBO;
+                const int jl = lane % NBO, il = lane / NBO;
+                for (int i0 = warp * RW * 4; i0 < R; i0 += ST_NW * RW * 4) {
+                    cplx v[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) v[q] = aug(i0 + q * RW + il, jl);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int i = i0 + q * RW + il;
+                        if (i < R) PB[i * NBO + (jl & ~7) + ((jl & 7) ^ swz(i & 7))] = v[q];
+                    }
+                }
+            } else
             for (int i = warp; i < rows; i += ST_NW) {
                 const cplx* src = A + (long long)(col0 + i) * LD + col0;
                 if (lane < NBO) PB[i * NBO + (lane & ~7) + ((lane & 7) ^ swz(i & 7))] = src[lane];
@@ -236,8 +283,8 @@ __global__ void __launch_bounds__(ST_NT, 1) sweep_stream_kernel(SweepParams p, i
             for (int ip = 0; ip < NCBP; ++ip) {
                 const int row0 = 8 * ip;
                 int* pvl = lp + row0;
-                if (SL > 1 && rows - row0 > ST_NT) panel_factor_mw<SL>(PB, NBO, rows, row0, tid, candk, candrow, pvl, info_sh, col0);
-                else panel_factor_mw<1>(PB, NBO, rows, row0, tid, candk, candrow, pvl, info_sh, col0);
+                if (SL > 1 && rows - row0 > ST_NT) panel_factor_mw<SL, ST_NW>(PB, NBO, rows, row0, tid, candk, candrow, pvl, info_sh, col0);
+                else panel_factor_mw<1, ST_NW>(PB, NBO, rows, row0, tid, candk, candrow, pvl, info_sh, col0);
                 __syncthreads();
                 // the exchanges also apply to the multipliers of the earlier inner panels (columns < row0): unlike in
                 // sweep_blocked.cu, L21 of the whole outer panel is an operand of the trailing update
@@ -282,22 +329,25 @@ __global__ void __launch_bounds__(ST_NT, 1) sweep_stream_kernel(SweepParams p, i
             for (int cc0 = col0 + NBO; cc0 < LD; cc0 += ST_CW) {
                 const int cw = min(ST_CW, LD - cc0);             // multiple of 8
                 {   // 4a. gather the moved rows (all loads, barrier, all stores); rows landing in the block go to UB
-                    const int c = tid & (ST_CW - 1), eg = tid >> 6;
-                    cplx vals[ST_MAXMOVED / 4];
+                    constexpr int NEG = ST_NT / ST_CW;             // row groups working side by side
+                    const int c = tid % ST_CW, eg = tid / ST_CW;
+                    constexpr int MAXMV = 2 * NBO;                 // rows the NBO exchanges can touch
+                    cplx vals[MAXMV / NEG];
 #pragma unroll
-                    for (int i = 0; i < ST_MAXMOVED / 4; ++i) {
-                        const int e = eg + 4 * i;
+                    for (int i = 0; i < MAXMV / NEG; ++i) {
+                        const int e = eg + NEG * i;
                         vals[i] = cmake(0.0, 0.0);
-                        if (e < ne && c < cw) vals[i] = A[(long long)(col0 + mv_src[e]) * LD + cc0 + c];
+                        if (first) { if (e < ne && c < cw && mv_dst[e] < NBO) vals[i] = aug(mv_src[e], cc0 + c); }
+                        else if (e < ne && c < cw) vals[i] = A[(long long)(col0 + mv_src[e]) * LD + cc0 + c];
                     }
                     __syncthreads();
 #pragma unroll
-                    for (int i = 0; i < ST_MAXMOVED / 4; ++i) {
-                        const int e = eg + 4 * i;
+                    for (int i = 0; i < MAXMV / NEG; ++i) {
+                        const int e = eg + NEG * i;
                         if (e < ne && c < cw) {
                             const int d = mv_dst[e];
                             if (d < NBO) UB[mphys(d, c, ST_CW)] = vals[i];
-                            else A[(long long)(col0 + d) * LD + cc0 + c] = vals[i];
+                            else if (!first) A[(long long)(col0 + d) * LD + cc0 + c] = vals[i];
                         }
                     }
                 }
@@ -356,11 +406,15 @@ __global__ void __launch_bounds__(ST_NT, 1) sweep_stream_kernel(SweepParams p, i
                     for (int kk = 0; kk < NBO / 4; ++kk) af[kk] = arow[(4 * kk + t) ^ sg];      // (4kk + t) ^ swz(g): same 8-block
                     cplx* crow = A + (long long)(col0 + 8 * rb + g) * LD + cc0 + 2 * t;
                     const int nct = cw / 8;
+                    const int srow = first ? idx[8 * rb + g] : 0;   // first step: the row the exchanges brought here
                     for (int ct0 = 0; ct0 < nct; ct0 += 4) {
                         cplx v[4][2];
 #pragma unroll
                         for (int q = 0; q < 4; ++q)
-                            if (ct0 + q < nct) { v[q][0] = crow[8 * (ct0 + q)]; v[q][1] = crow[8 * (ct0 + q) + 1]; }
+                            if (ct0 + q < nct) {
+                                if (first) { v[q][0] = aug(srow, cc0 + 2 * t + 8 * (ct0 + q)); v[q][1] = aug(srow, cc0 + 2 * t + 8 * (ct0 + q) + 1); }
+                                else { v[q][0] = crow[8 * (ct0 + q)]; v[q][1] = crow[8 * (ct0 + q) + 1]; }
+                            }
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
                             if (ct0 + q < nct) {
@@ -388,7 +442,7 @@ __global__ void __launch_bounds__(ST_NT, 1) sweep_stream_kernel(SweepParams p, i
         // small solve plus two CTA barriers -- no DRAM round trip.
         cplx* xs = PB;                                            // R x m, xs[k * m + c]
         cplx* dblk = UB;                                          // 8 x 8 diagonal block (row-major)
-        constexpr int RPT = (NBO == 32) ? 1 : 2;                  // rows per thread (R <= 256 RPT)
+        constexpr int RPT = RMAX / ST_NT;                         // rows per thread (R <= ST_NT RPT)
         for (int e = tid; e < R * m; e += ST_NT) { const int i = e / m, c = e - i * m; xs[e] = A[(long long)i * LD + R + c]; }
         cplx un[RPT][8], dn = cmake(0.0, 0.0);
         {
@@ -470,29 +524,43 @@ __global__ void __launch_bounds__(ST_NT, 1) sweep_stream_kernel(SweepParams p, i
     }
 }
 
-struct StreamGeom { int R, LD, NBO; size_t smem; };
+struct StreamGeom { int R, LD, NBO, NW, CW, MINB; size_t smem; };
 
+// Geometry per size.  Several CTAs per SM, so that one CTA's latency-bound phases (pivot search, gathers, U12 solves)
+// run under another's DMMA update: R <= 128: three 4-warp CTAs (1.11 M points/s at r = 128 against 0.79 M for one 8-warp
+// CTA), R <= 256: two 8-warp CTAs with 16-column outer panels (231 k points/s at r = 256 against 200 k), R > 256: one
+// 8-warp CTA.  MF_STREAM_CFG selects a geometry by hand for measurements: 0 = one CTA per SM with 32-column panels,
+// 1 = two 8-warp CTAs, 2 = three 4-warp CTAs, 3 = two 4-warp CTAs.
 StreamGeom stream_geom(int r, int m) {
     StreamGeom gm;
     gm.R = (r + 31) / 32 * 32;                                   // multiple of both outer panel widths
     gm.LD = gm.R + (m + 7) / 8 * 8;
-    gm.NBO = gm.R <= 256 ? 32 : 16;
-    gm.smem = sizeof(cplx) * ((size_t)gm.R * gm.NBO + (size_t)gm.NBO * ST_CW + 2 * ST_NW * 8) + sizeof(CandKey) * 2 * ST_NW
+    int cfg = gm.R <= MF_STREAM_SMALL_R ? 2 : 1;
+    if (const char* e = getenv("MF_STREAM_CFG")) cfg = atoi(e);
+    if (gm.R > 256) cfg = 9;
+    switch (cfg) {
+        case 1:  gm.NBO = 16; gm.NW = 8; gm.CW = 64; gm.MINB = 2; break;
+        case 2:  gm.NBO = 16; gm.NW = 4; gm.CW = 32; gm.MINB = 3; break;
+        case 3:  gm.NBO = 16; gm.NW = 4; gm.CW = 64; gm.MINB = 2; break;
+        case 9:  gm.NBO = 16; gm.NW = 8; gm.CW = 64; gm.MINB = 1; break;
+        default: gm.NBO = 32; gm.NW = 8; gm.CW = 64; gm.MINB = 1; break;
+    }
+    gm.smem = sizeof(cplx) * ((size_t)gm.R * gm.NBO + (size_t)gm.NBO * gm.CW + 2 * ST_MAXNW * 8) + sizeof(CandKey) * 2 * ST_MAXNW
             + sizeof(int) * ((size_t)gm.R + 2 * ST_MAXMOVED + gm.NBO + 2) + 64;
     return gm;
 }
 
-template <int NBO, int SL>
+template <int NBO, int NW, int CW, int RMAX, int MINB, bool FUSE>
 int launch_stream(SweepParams p, const StreamGeom& gm, size_t ws_bytes, cudaStream_t stream) {
-    auto kern = sweep_stream_kernel<NBO, SL>;
+    auto kern = sweep_stream_kernel<NBO, NW, CW, RMAX, MINB, FUSE>;
     MF_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gm.smem));
     const size_t slot = sizeof(cplx) * (size_t)gm.R * gm.LD;
-    long long grid = mf_num_sms();
+    long long grid = (long long)mf_num_sms() * MINB;
     if (grid > p.F) grid = p.F;
     if ((long long)(ws_bytes / slot) < grid) grid = (long long)(ws_bytes / slot);
     if (grid < 1 || !p.ws) MF_FAIL_ARG(21, "workspace too small for the streamed blocked sweep (see mf_sweep_ws_bytes)");
     p.ws_stride = (long long)gm.R * gm.LD;
-    kern<<<(unsigned)grid, ST_NT, gm.smem, stream>>>(p, gm.R, gm.LD);
+    kern<<<(unsigned)grid, NW * 32, gm.smem, stream>>>(p, gm.R, gm.LD);
     MF_CHECK_LAUNCH();
     if (p.S) return gsm_finish_launch(p.S, p.m, p.F, stream);
     return 0;
@@ -508,12 +576,21 @@ bool sweep_stream_supports(int r, int m) {
 
 size_t sweep_stream_ws_bytes(int r, int m, long long F) {
     const StreamGeom gm = stream_geom(r, m);
-    long long grid = mf_num_sms(); if (grid > F) grid = F; if (grid < 1) grid = 1;
+    long long grid = (long long)mf_num_sms() * gm.MINB; if (grid > F) grid = F; if (grid < 1) grid = 1;
     return sizeof(cplx) * (size_t)gm.R * gm.LD * (size_t)grid;
 }
 
 int sweep_stream_launch(const SweepParams& p, size_t ws_bytes, cudaStream_t stream) {
     const StreamGeom gm = stream_geom(p.r, p.m);
-    if (gm.NBO == 32) return launch_stream<32, 1>(p, gm, ws_bytes, stream);
-    return launch_stream<16, 2>(p, gm, ws_bytes, stream);
+    bool fuse = MF_STREAM_DEFAULT_FUSE;
+    if (const char* e = getenv("MF_STREAM_FUSE")) fuse = atoi(e) != 0;
+#define MF_STREAM_CASE(NBO, NW, CW, RMAX, MINB)                                                        \
+    return fuse ? launch_stream<NBO, NW, CW, RMAX, MINB, true>(p, gm, ws_bytes, stream)                 \
+                : launch_stream<NBO, NW, CW, RMAX, MINB, false>(p, gm, ws_bytes, stream)
+    if (gm.R > 256) { MF_STREAM_CASE(16, 8, 64, 512, 1); }
+    if (gm.NW == 8 && gm.MINB == 2) { MF_STREAM_CASE(16, 8, 64, 256, 2); }
+    if (gm.NW == 4 && gm.MINB == 3) { MF_STREAM_CASE(16, 4, 32, 256, 3); }
+    if (gm.NW == 4) { MF_STREAM_CASE(16, 4, 64, 256, 2); }
+    MF_STREAM_CASE(32, 8, 64, 256, 1);
+#undef MF_STREAM_CASE
 }

@@ -69,7 +69,7 @@ def test_sweep_matches_live_reference_fixture(dv, name):
 
 
 @pytest.mark.parametrize("r,m,nf", [(1, 1, 3), (2, 2, 5), (7, 3, 33), (16, 16, 9), (31, 5, 40), (48, 2, 300), (100, 8, 12), (112, 16, 5),
-                                    (113, 1, 4), (128, 4, 20), (200, 2, 6), (257, 9, 3), (384, 16, 2), (512, 4, 150)])
+                                    (113, 1, 4), (128, 4, 20), (160, 3, 500), (200, 2, 6), (256, 4, 10), (257, 9, 3), (384, 16, 2), (512, 4, 150)])
 def test_sweep_matches_oracle_on_seeded_models(dv, r, m, nf):
     from morfem_b200 import synthetic
     a0, a1, a2, b = synthetic.reduced_model(r, m, seed=100 + r)
