@@ -49,6 +49,11 @@ int mf_gemm_tn_c128(const mf_c128* A, int64_t lda, int ra, const mf_c128* B, int
  * the lift Q x.  Out must not alias A. */
 int mf_gemm_nn_c128(const mf_c128* A, int64_t lda, int64_t n, int ra, const mf_c128* W, int64_t ldw, int rb,
                     mf_c128* Out, int64_t ldo, void* stream);
+/* Out (n x r) = A (n x r) * W with W (r x r) UPPER TRIANGULAR -- the `X R^-1` application of a Cholesky-QR pass
+ * (stage 1, implementation.py:226).  Entries of W below the diagonal are taken as zero and whole 64-column tiles of
+ * zero products are skipped (5/8 of the work at r = 256); results equal mf_gemm_nn on a W whose lower part is zero. */
+int mf_trmm_nn_c128(const mf_c128* A, int64_t lda, int64_t n, int r, const mf_c128* W, int64_t ldw,
+                    mf_c128* Out, int64_t ldo, void* stream);
 
 /* ---- r x r factorisations used by the basis stage (all single-launch, device-resident) ---------------
  * mf_equilibrate:   d[j] = 1/sqrt(real(G[j][j])) (1 if the diagonal is not positive); G <- diag(d) G diag(d)
@@ -109,6 +114,8 @@ size_t mf_gemm_tn_f64_ws_bytes(int ra, int rb, int64_t n);
 int mf_gemm_tn_f64(const double* A, int64_t lda, int ra, const double* B, int64_t ldb, int rb, int64_t n,
                    double* C, int64_t ldc, void* ws, size_t ws_bytes, void* stream);
 int mf_gemm_nn_f64(const double* A, int64_t lda, int64_t n, int ra, const double* W, int64_t ldw, int rb,
+                   double* Out, int64_t ldo, void* stream);
+int mf_trmm_nn_f64(const double* A, int64_t lda, int64_t n, int r, const double* W, int64_t ldw,
                    double* Out, int64_t ldo, void* stream);
 int mf_spmm_csr_f64(const int32_t* rowptr, const int32_t* colidx, const double* vals, int64_t nrows,
                     const double* Q, int64_t ldq, int r, double* Y, int64_t ldy, void* stream);

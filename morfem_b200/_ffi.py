@@ -26,6 +26,8 @@ SIGNATURES = {
     "mf_gemm_tn_c128": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int64, c_int, c_int64, c_int, c_void_p, c_int64,
                                 c_void_p, c_size_t, c_void_p]),
     "mf_gemm_nn_c128": (c_int, [c_void_p, c_int64, c_int64, c_int, c_void_p, c_int64, c_int, c_void_p, c_int64, c_void_p]),
+    "mf_trmm_nn_c128": (c_int, [c_void_p, c_int64, c_int64, c_int, c_void_p, c_int64, c_void_p, c_int64, c_void_p]),
+    "mf_trmm_nn_f64": (c_int, [c_void_p, c_int64, c_int64, c_int, c_void_p, c_int64, c_void_p, c_int64, c_void_p]),
     "mf_equilibrate_c128": (c_int, [c_void_p, c_int64, c_int, c_double, c_void_p, c_void_p, c_void_p]),
     "mf_potrf_upper_c128": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p]),
     "mf_trtri_upper_c128": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int64, c_void_p]),

@@ -168,7 +168,7 @@ constexpr int NN_STAGE_ELEMS = NN_TM * NN_LDA + KC * NN_LDW;
 
 __global__ void __launch_bounds__(NN_THREADS, 1)
 gemm_nn_kernel(const cplx* __restrict__ A, long long lda, long long n, int ra, const cplx* __restrict__ W, long long ldw, int rb,
-               cplx* __restrict__ Out, long long ldo) {
+               cplx* __restrict__ Out, long long ldo, int w_upper) {
     extern __shared__ __align__(16) cplx smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
@@ -176,7 +176,9 @@ gemm_nn_kernel(const cplx* __restrict__ A, long long lda, long long n, int ra, c
     const int ntn = (rb + NN_TN - 1) / NN_TN;
     const long long tm = blockIdx.x / ntn; const int tn = (int)(blockIdx.x - tm * ntn);
     const long long m0 = tm * NN_TM; const int j0 = tn * NN_TN;
-    const int nchunks = (ra + KC - 1) / KC;
+    // upper-triangular W (the R^-1 of a Cholesky-QR pass): rows k >= j0 + NN_TN of this column tile are zero, skip them
+    const int kmax = (w_upper && j0 + NN_TN < ra) ? j0 + NN_TN : ra;
+    const int nchunks = (kmax + KC - 1) / KC;
 
     auto load_stage = [&](int stage, int chunk) {
         cplx* As = smem + stage * NN_STAGE_ELEMS;
@@ -286,8 +288,8 @@ extern "C" int mf_gemm_tn_c128(const mf_c128* A, int64_t lda, int ra, const mf_c
     return 0;
 }
 
-extern "C" int mf_gemm_nn_c128(const mf_c128* A, int64_t lda, int64_t n, int ra, const mf_c128* W, int64_t ldw, int rb,
-                               mf_c128* Out, int64_t ldo, void* stream) {
+static int gemm_nn_c128_impl(const mf_c128* A, int64_t lda, int64_t n, int ra, const mf_c128* W, int64_t ldw, int rb,
+                            mf_c128* Out, int64_t ldo, void* stream, int w_upper) {
     if (!A) MF_FAIL_ARG(1, "A is NULL");
     if (ra <= 0 || lda < ra) MF_FAIL_ARG(4, "need 0 < ra <= lda");
     if (n < 0) MF_FAIL_ARG(3, "n < 0");
@@ -303,7 +305,17 @@ extern "C" int mf_gemm_nn_c128(const mf_c128* A, int64_t lda, int64_t n, int ra,
     int tiles_n = (rb + NN_TN - 1) / NN_TN;
     long long grid = tiles_m * tiles_n;
     if (grid > 0x7fffffffLL) MF_FAIL_ARG(3, "n too large for one launch");
-    gemm_nn_kernel<<<(unsigned)grid, NN_THREADS, smem, st>>>((const cplx*)A, lda, n, ra, (const cplx*)W, ldw, rb, (cplx*)Out, ldo);
+    gemm_nn_kernel<<<(unsigned)grid, NN_THREADS, smem, st>>>((const cplx*)A, lda, n, ra, (const cplx*)W, ldw, rb, (cplx*)Out, ldo, w_upper);
     MF_CHECK_LAUNCH();
     return 0;
+}
+
+extern "C" int mf_gemm_nn_c128(const mf_c128* A, int64_t lda, int64_t n, int ra, const mf_c128* W, int64_t ldw, int rb,
+                               mf_c128* Out, int64_t ldo, void* stream) {
+    return gemm_nn_c128_impl(A, lda, n, ra, W, ldw, rb, Out, ldo, stream, 0);
+}
+
+extern "C" int mf_trmm_nn_c128(const mf_c128* A, int64_t lda, int64_t n, int r, const mf_c128* W, int64_t ldw,
+                               mf_c128* Out, int64_t ldo, void* stream) {
+    return gemm_nn_c128_impl(A, lda, n, r, W, ldw, r, Out, ldo, stream, 1);
 }

@@ -174,7 +174,7 @@ constexpr int NN_STAGE_ELEMS = NN_TM * NN_LDA + KC * NN_LDW;
 
 __global__ void __launch_bounds__(NN_THREADS, 2)
 gemm_nn_f64_kernel(const double* __restrict__ A, long long lda, long long n, int ra, const double* __restrict__ W, long long ldw, int rb,
-                   double* __restrict__ Out, long long ldo) {
+                   double* __restrict__ Out, long long ldo, int w_upper) {
     extern __shared__ __align__(16) double smem_d[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
@@ -182,7 +182,8 @@ gemm_nn_f64_kernel(const double* __restrict__ A, long long lda, long long n, int
     const int ntn = (rb + NN_TN - 1) / NN_TN;
     const long long tm = blockIdx.x / ntn; const int tn = (int)(blockIdx.x - tm * ntn);
     const long long m0 = tm * NN_TM; const int j0 = tn * NN_TN;
-    const int nchunks = (ra + KC - 1) / KC;
+    const int kmax = (w_upper && j0 + NN_TN < ra) ? j0 + NN_TN : ra;      // upper-triangular W: rows below the tile are zero
+    const int nchunks = (kmax + KC - 1) / KC;
 
     auto load_stage = [&](int stage, int chunk) {
         double* As = smem_d + stage * NN_STAGE_ELEMS;
@@ -281,8 +282,8 @@ extern "C" int mf_gemm_tn_f64(const double* A, int64_t lda, int ra, const double
     return 0;
 }
 
-extern "C" int mf_gemm_nn_f64(const double* A, int64_t lda, int64_t n, int ra, const double* W, int64_t ldw, int rb,
-                              double* Out, int64_t ldo, void* stream) {
+static int gemm_nn_f64_impl(const double* A, int64_t lda, int64_t n, int ra, const double* W, int64_t ldw, int rb,
+                           double* Out, int64_t ldo, void* stream, int w_upper) {
     if (!A) MF_FAIL_ARG(1, "A is NULL");
     if (ra <= 0 || lda < ra) MF_FAIL_ARG(4, "need 0 < ra <= lda");
     if (n < 0) MF_FAIL_ARG(3, "n < 0");
@@ -298,7 +299,17 @@ extern "C" int mf_gemm_nn_f64(const double* A, int64_t lda, int64_t n, int ra, c
     const int tiles_n = (rb + NN_TN - 1) / NN_TN;
     const long long grid = tiles_m * tiles_n;
     if (grid > 0x7fffffffLL) MF_FAIL_ARG(3, "n too large for one launch");
-    gemm_nn_f64_kernel<<<(unsigned)grid, NN_THREADS, smem, st>>>(A, lda, n, ra, W, ldw, rb, Out, ldo);
+    gemm_nn_f64_kernel<<<(unsigned)grid, NN_THREADS, smem, st>>>(A, lda, n, ra, W, ldw, rb, Out, ldo, w_upper);
     MF_CHECK_LAUNCH();
     return 0;
+}
+
+extern "C" int mf_gemm_nn_f64(const double* A, int64_t lda, int64_t n, int ra, const double* W, int64_t ldw, int rb,
+                              double* Out, int64_t ldo, void* stream) {
+    return gemm_nn_f64_impl(A, lda, n, ra, W, ldw, rb, Out, ldo, stream, 0);
+}
+
+extern "C" int mf_trmm_nn_f64(const double* A, int64_t lda, int64_t n, int r, const double* W, int64_t ldw,
+                              double* Out, int64_t ldo, void* stream) {
+    return gemm_nn_f64_impl(A, lda, n, r, W, ldw, r, Out, ldo, stream, 1);
 }

@@ -168,8 +168,9 @@ def gemm_tn(a: torch.Tensor, b: torch.Tensor, conj: bool = False, out: Optional[
     return out
 
 
-def gemm_nn(a: torch.Tensor, w: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """``a @ w`` for a tall ``a`` (n x ra) and a small ``w`` (ra x rb).  float64 operands run the real twin."""
+def gemm_nn(a: torch.Tensor, w: torch.Tensor, out: Optional[torch.Tensor] = None, w_upper: bool = False) -> torch.Tensor:
+    """``a @ w`` for a tall ``a`` (n x ra) and a small ``w`` (ra x rb).  float64 operands run the real twin.
+    ``w_upper``: ``w`` is square upper triangular (the ``R^-1`` of a Cholesky-QR pass) -- zero tiles are skipped."""
     lib = _ffi.load()
     _check_mat(a, "a"); _check_mat(w, "w")
     real = _same_dtype(a, w, "gemm_nn")
@@ -179,6 +180,20 @@ def gemm_nn(a: torch.Tensor, w: torch.Tensor, out: Optional[torch.Tensor] = None
     rb = w.shape[1]
     if out is None:
         out = torch.empty((n, rb), dtype=a.dtype, device=a.device)
+    if w_upper:
+        if rb != ra:
+            raise ValueError("gemm_nn: w_upper needs a square w")
+        tiles = (ra + 63) // 64                    # 64-column output tiles; tile j multiplies (j + 1) * 64 rows of w
+        frac = (tiles + 1) / (2.0 * tiles)
+        if real:
+            with _timed("gemm_nn", nbytes=8.0 * n * (ra + rb) + 8.0 * ra * rb, flops=2.0 * n * ra * rb * frac):
+                _ffi.check(lib.mf_trmm_nn_f64(_ptr(a), a.stride(0), n, ra, _ptr(w), w.stride(0), _ptr(out), out.stride(0), _stream()),
+                           "mf_trmm_nn_f64")
+        else:
+            with _timed("gemm_nn", nbytes=16.0 * n * (ra + rb) + 16.0 * ra * rb, flops=8.0 * n * ra * rb * frac):
+                _ffi.check(lib.mf_trmm_nn_c128(_ptr(a), a.stride(0), n, ra, _ptr(w), w.stride(0), _ptr(out), out.stride(0), _stream()),
+                           "mf_trmm_nn_c128")
+        return out
     if real:
         with _timed("gemm_nn", nbytes=8.0 * n * (ra + rb) + 8.0 * ra * rb, flops=2.0 * n * ra * rb):
             _ffi.check(lib.mf_gemm_nn_f64(_ptr(a), a.stride(0), n, ra, _ptr(w), w.stride(0), rb, _ptr(out), out.stride(0), _stream()),
@@ -529,7 +544,7 @@ def _cholesky_qr2_optimistic(s: torch.Tensor, group=None) -> CholQR:
         rinv = _trtri_upper(g)
         r_tot = g if r_tot is None else gemm_nn(g, r_tot)
         if p == 0:
-            x = gemm_nn(x, _like_block(rinv, x))
+            x = gemm_nn(x, _like_block(rinv, x), w_upper=True)
     return CholQR(x, r_tot, rinv, 2, [0.0, 0.0], flags)
 
 
@@ -581,7 +596,7 @@ def cholesky_qr(s: torch.Tensor, group=None, max_passes: int = 6, optimistic: bo
         tgt = p % 2
         if bufs[tgt] is None:
             bufs[tgt] = torch.empty((n_loc, r), dtype=s.dtype, device=dev)
-        x = gemm_nn(x, _like_block(rinv, x), out=bufs[tgt])
+        x = gemm_nn(x, _like_block(rinv, x), out=bufs[tgt], w_upper=True)
     raise AssertionError("unreachable")
 
 

@@ -48,6 +48,8 @@ def test_argument_validation_without_gpu():
     # the real float64 twins and the row-grouped SpMM entries validate the same way
     assert lib.mf_gemm_tn_f64(None, 4, 4, None, 4, 4, 10, None, 4, None, 0, None) == -1 and b"mf_gemm_tn_f64" in lib.mf_last_error()
     assert lib.mf_gemm_nn_f64(None, 4, 10, 4, None, 4, 4, None, 4, None) == -1
+    assert lib.mf_trmm_nn_f64(None, 4, 10, 4, None, 4, None, 4, None) == -1
+    assert lib.mf_trmm_nn_c128(None, 4, 10, 4, None, 4, None, 4, None) == -1
     assert lib.mf_spmm_csr_f64(None, None, None, 10, None, 4, 4, None, 4, None) == -1
     assert lib.mf_spmm_group_count(None, None, 10, 4, None, None) == -1
     assert lib.mf_spmm_grouped_c128(None, None, None, 10, 4, None, 4, 4, None, 4, None) == -1

@@ -54,6 +54,25 @@ def test_gemm_nn(dv, n, ra, rb):
     assert rel(out, a @ w) < 1e-13
 
 
+@pytest.mark.parametrize("n,r", [(300, 5), (129, 64), (1000, 65), (700, 200), (260, 256), (150, 512)])
+def test_triangular_apply_skips_zero_tiles_and_equals_gemm_nn(dv, n, r):
+    """X R^-1 with an upper-triangular factor (mf_trmm_nn_*): whatever sits below the diagonal tiles is never read, and
+    the result equals the full product with a clean triangular factor -- bit for bit -- in both arithmetic types."""
+    rng = np.random.default_rng(n + r)
+    a, w = crandn(rng, n, r), np.triu(crandn(rng, r, r))
+    dirty = w.copy()
+    for j0 in range(0, r, 64):                                   # garbage below the 64-column diagonal tiles
+        dirty[j0 + 64:, j0:j0 + 64] = 1e300
+    full = dv.gemm_nn(dv.to_device_c128(a), dv.to_device_c128(w)).cpu().numpy()
+    tri = dv.gemm_nn(dv.to_device_c128(a), dv.to_device_c128(dirty), w_upper=True).cpu().numpy()
+    assert np.array_equal(full, tri)
+    assert rel(tri, a @ w) < 1e-13
+    up = lambda x: torch.from_numpy(np.ascontiguousarray(x)).cuda()
+    full_r = dv.gemm_nn(up(a.real), up(w.real)).cpu().numpy()
+    tri_r = dv.gemm_nn(up(a.real), up(dirty.real), w_upper=True).cpu().numpy()
+    assert np.array_equal(full_r, tri_r) and rel(tri_r, a.real @ w.real) < 1e-14
+
+
 @pytest.mark.parametrize("r", [1, 2, 7, 16, 33, 64, 150])
 def test_cholesky_and_triangular_inverse(dv, r):
     from morfem_b200 import _ffi
