@@ -257,23 +257,22 @@ __global__ void __launch_bounds__(ST_NW * 32, MINB) sweep_stream_kernel(SweepPar
             const int rows = R - col0;                           // rows (and local row count) of the outer panel
             // 1. outer panel -> shared memory
             const bool first = FUSE && col0 == 0;
-            if (first) {                                         // 32 / NBO rows per warp instruction, four of those in flight
+            {                                                    // 32 / NBO rows per warp instruction, four of those in flight
                 constexpr int RW = 32 / NBO;
                 const int jl = lane % NBO, il = lane / NBO;
-                for (int i0 = warp * RW * 4; i0 < R; i0 += ST_NW * RW * 4) {
+                for (int i0 = warp * RW * 4; i0 < rows; i0 += ST_NW * RW * 4) {
                     cplx v[4];
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) v[q] = aug(i0 + q * RW + il, jl);
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
                         const int i = i0 + q * RW + il;
-                        if (i < R) PB[i * NBO + (jl & ~7) + ((jl & 7) ^ swz(i & 7))] = v[q];
+                        if (i < rows) v[q] = first ? aug(i, jl) : A[(long long)(col0 + i) * LD + col0 + jl];
+                    }
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int i = i0 + q * RW + il;
+                        if (i < rows) PB[i * NBO + (jl & ~7) + ((jl & 7) ^ swz(i & 7))] = v[q];
                     }
                 }
-            } else
-            for (int i = warp; i < rows; i += ST_NW) {
-                const cplx* src = A + (long long)(col0 + i) * LD + col0;
-                if (lane < NBO) PB[i * NBO + (lane & ~7) + ((lane & 7) ^ swz(i & 7))] = src[lane];
             }
             for (int i = tid; i < rows; i += ST_NT) idx[i] = i;
             if (tid == 0) *nmoved = 0;
@@ -398,23 +397,34 @@ __global__ void __launch_bounds__(ST_NW * 32, MINB) sweep_stream_kernel(SweepPar
                     const int j = e / cw, c = e - j * cw;
                     A[(long long)(col0 + j) * LD + cc0 + c] = UB[mphys(j, c, ST_CW)];
                 }
-                // 4d. A22 += (-L21) U12: one row block per warp iteration, A fragments kept in registers
-                for (int rb = NCBP + warp; rb < rows / 8; rb += ST_NW) {
-                    const cplx* arow = PB + (8 * rb + g) * NBO;
-                    cplx af[NBO / 4];
+                // 4d. A22 += (-L21) U12.  Work unit = (row block, batch of <= 4 column tiles), dealt round-robin to the warps;
+                // two register buffers: the C tiles of the next unit are in flight while the DMMAs of the current one run.
+                {
+                    const int nct = cw / 8, nbt = (nct + 3) >> 2;
+                    const int nunits = (rows / 8 - NCBP) * nbt;
+                    auto issue = [&](const int u, cplx (&v)[4][2]) {
+                        const int rbi = u / nbt, ct0 = (u - rbi * nbt) * 4;
+                        const int row = 8 * (NCBP + rbi) + g;    // local row of the outer panel
+                        if (first) {                             // first step: the row the exchanges brought here, from the operators
+                            const int srow = idx[row];
 #pragma unroll
-                    for (int kk = 0; kk < NBO / 4; ++kk) af[kk] = arow[(4 * kk + t) ^ sg];      // (4kk + t) ^ swz(g): same 8-block
-                    cplx* crow = A + (long long)(col0 + 8 * rb + g) * LD + cc0 + 2 * t;
-                    const int nct = cw / 8;
-                    const int srow = first ? idx[8 * rb + g] : 0;   // first step: the row the exchanges brought here
-                    for (int ct0 = 0; ct0 < nct; ct0 += 4) {
-                        cplx v[4][2];
+                            for (int q = 0; q < 4; ++q)
+                                if (ct0 + q < nct) { v[q][0] = aug(srow, cc0 + 2 * t + 8 * (ct0 + q)); v[q][1] = aug(srow, cc0 + 2 * t + 8 * (ct0 + q) + 1); }
+                        } else {
+                            const cplx* crow = A + (long long)(col0 + row) * LD + cc0 + 2 * t;
 #pragma unroll
-                        for (int q = 0; q < 4; ++q)
-                            if (ct0 + q < nct) {
-                                if (first) { v[q][0] = aug(srow, cc0 + 2 * t + 8 * (ct0 + q)); v[q][1] = aug(srow, cc0 + 2 * t + 8 * (ct0 + q) + 1); }
-                                else { v[q][0] = crow[8 * (ct0 + q)]; v[q][1] = crow[8 * (ct0 + q) + 1]; }
-                            }
+                            for (int q = 0; q < 4; ++q)
+                                if (ct0 + q < nct) { v[q][0] = crow[8 * (ct0 + q)]; v[q][1] = crow[8 * (ct0 + q) + 1]; }
+                        }
+                    };
+                    auto compute = [&](const int u, cplx (&v)[4][2]) {
+                        const int rbi = u / nbt, ct0 = (u - rbi * nbt) * 4;
+                        const int row = 8 * (NCBP + rbi) + g;
+                        const cplx* arow = PB + row * NBO;
+                        cplx af[NBO / 4];
+#pragma unroll
+                        for (int kk = 0; kk < NBO / 4; ++kk) af[kk] = arow[(4 * kk + t) ^ sg];      // (4kk + t) ^ swz(g): same 8-block
+                        cplx* crow = A + (long long)(col0 + row) * LD + cc0 + 2 * t;
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
                             if (ct0 + q < nct) {
@@ -427,6 +437,50 @@ __global__ void __launch_bounds__(ST_NW * 32, MINB) sweep_stream_kernel(SweepPar
                                     dmma884(cre0, cre1, -af[kk].y, b.y); dmma884(cim0, cim1, af[kk].y, b.x);
                                 }
                                 crow[8 * ct] = cmake(cre0, cim0); crow[8 * ct + 1] = cmake(cre1, cim1);
+                            }
+                        }
+                    };
+                    if (MINB == 1) {                             // register budget of a lone CTA: two buffers
+                        cplx va[4][2], vb[4][2];
+                        int u = warp;
+                        if (u < nunits) issue(u, va);
+                        for (; u < nunits; u += 2 * ST_NW) {
+                            if (u + ST_NW < nunits) issue(u + ST_NW, vb);
+                            compute(u, va);
+                            if (u + 2 * ST_NW < nunits) issue(u + 2 * ST_NW, va);
+                            if (u + ST_NW < nunits) compute(u + ST_NW, vb);
+                        }
+                    } else {                                     // several CTAs per SM hide the load latency for each other:
+                        // one row block per warp iteration, A fragments kept in registers across its column tiles
+                        for (int rb = NCBP + warp; rb < rows / 8; rb += ST_NW) {
+                            const cplx* arow = PB + (8 * rb + g) * NBO;
+                            cplx af[NBO / 4];
+#pragma unroll
+                            for (int kk = 0; kk < NBO / 4; ++kk) af[kk] = arow[(4 * kk + t) ^ sg];
+                            cplx* crow = A + (long long)(col0 + 8 * rb + g) * LD + cc0 + 2 * t;
+                            const int srow = first ? idx[8 * rb + g] : 0;
+                            for (int ct0 = 0; ct0 < nct; ct0 += 4) {
+                                cplx v[4][2];
+#pragma unroll
+                                for (int q = 0; q < 4; ++q)
+                                    if (ct0 + q < nct) {
+                                        if (first) { v[q][0] = aug(srow, cc0 + 2 * t + 8 * (ct0 + q)); v[q][1] = aug(srow, cc0 + 2 * t + 8 * (ct0 + q) + 1); }
+                                        else { v[q][0] = crow[8 * (ct0 + q)]; v[q][1] = crow[8 * (ct0 + q) + 1]; }
+                                    }
+#pragma unroll
+                                for (int q = 0; q < 4; ++q) {
+                                    if (ct0 + q < nct) {
+                                        const int ct = ct0 + q;
+                                        double cre0 = v[q][0].x, cre1 = v[q][1].x, cim0 = v[q][0].y, cim1 = v[q][1].y;
+#pragma unroll
+                                        for (int kk = 0; kk < NBO / 4; ++kk) {
+                                            const cplx b = UB[(4 * kk + t) * ST_CW + 8 * ct + (g ^ swz((4 * kk + t) & 7))];
+                                            dmma884(cre0, cre1, af[kk].x, b.x); dmma884(cim0, cim1, af[kk].x, b.y);
+                                            dmma884(cre0, cre1, -af[kk].y, b.y); dmma884(cim0, cim1, af[kk].y, b.x);
+                                        }
+                                        crow[8 * ct] = cmake(cre0, cim0); crow[8 * ct + 1] = cmake(cre1, cim1);
+                                    }
+                                }
                             }
                         }
                     }
