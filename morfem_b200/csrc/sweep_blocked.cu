@@ -263,7 +263,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) sweep_blocked_kernel(SweepParam
                             const cplx* urow = M + (kb8 + j) * LD + kb8;
                             const int sw = swz(j);
 #pragma unroll
-                            for (int jj = j + 1; jj < 8; ++jj) cfms(x[j], urow[jj ^ sw], x[jj]);
+                            for (int jj = 7; jj > j; --jj) cfms(x[j], urow[jj ^ sw], x[jj]);   // newest unknown last (ztrsm order): short dependent chain
                             x[j] = cmul(x[j], urow[j ^ sw]);             // reciprocal pivot on the diagonal
                         }
 #pragma unroll

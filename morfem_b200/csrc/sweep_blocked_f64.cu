@@ -290,7 +290,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) sweep_blocked_f64_kernel(SweepP
                             const double* urow = M + (kb8 + j) * LD + kb8;
                             const int sw = rswz(j);
 #pragma unroll
-                            for (int jj = j + 1; jj < 8; ++jj) x[j] = fma(-urow[jj ^ sw], x[jj], x[j]);
+                            for (int jj = 7; jj > j; --jj) x[j] = fma(-urow[jj ^ sw], x[jj], x[j]);   // newest unknown last (dtrsm order)
                             x[j] *= urow[j ^ sw];                    // reciprocal pivot on the diagonal
                         }
 #pragma unroll

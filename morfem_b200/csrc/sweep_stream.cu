@@ -537,7 +537,7 @@ __global__ void __launch_bounds__(ST_NW * 32, MINB) sweep_stream_kernel(SweepPar
 #pragma unroll
                 for (int j = 7; j >= 0; --j) {
 #pragma unroll
-                    for (int jj = j + 1; jj < 8; ++jj) cfms(x[j], dblk[j * 8 + jj], x[jj]);
+                    for (int jj = 7; jj > j; --jj) cfms(x[j], dblk[j * 8 + jj], x[jj]);   // newest unknown last (ztrsm order)
                     x[j] = cmul(x[j], dblk[j * 8 + j]);           // reciprocal pivot on the diagonal
                 }
 #pragma unroll
