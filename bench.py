@@ -360,6 +360,22 @@ def run_b200(args, wl, rank, world, local_rank):
         e2e = {"value": f_total / dt, "unit": UNIT, "h2d_bytes_per_step": dv.transfer_bytes["h2d"] // k_e2e,
                "d2h_bytes_per_step": dv.transfer_bytes["d2h"] // k_e2e, "ms_per_step": dt * 1e3, "steps": k_e2e,
                "call": "morfem_b200.test_helpers.model_order_reduction_gsm_from_snapshots (host ndarrays / scipy csc in pinned memory)"}
+        # PCIe floor of that call: nothing but the same pinned host buffers copied to the device (what bounds e2e)
+        bufs = [torch.from_numpy(s_host)] + [torch.from_numpy(np.asarray(x)) for a_ in (c_host, g_host, b_host) for x in (a_.data, a_.indices, a_.indptr)]
+        dsts = [torch.empty_like(b_, device=dev) for b_ in bufs]
+        torch.cuda.synchronize()
+        c0_, c1_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0_.record()
+        for _ in range(3):
+            for d_, b_ in zip(dsts, bufs):
+                d_.copy_(b_, non_blocking=True)
+        c1_.record()
+        torch.cuda.synchronize()
+        copy_ms = c0_.elapsed_time(c1_) / 3
+        copy_bytes = sum(b_.numel() * b_.element_size() for b_ in bufs)
+        e2e["h2d_copy_floor"] = {"ms": copy_ms, "bytes": copy_bytes, "GBps": copy_bytes / copy_ms / 1e6,
+                                 "note": "the same pinned input buffers copied host->device with nothing else running"}
+        del dsts
         # the same call with the FEM operators kept on the device between calls (the model is fixed, the snapshot block is
         # the per-step input): H2D = the snapshot block only
         for _ in range(2):
@@ -408,6 +424,24 @@ def run_b200(args, wl, rank, world, local_rank):
                                   f"stages 3+4 on {tcpu['points_sampled']} of {f.size} points ({tcpu['sweep_s_per_point'] * 1e6:.0f} + "
                                   f"{tcpu['gsm_s_per_point'] * 1e6:.0f} us/point) scaled linearly; real float64 like the reference"}
 
+    # ---- stages 1+2 inside the timed step against their composite roofline: per kernel
+    #      max(algorithmic bytes / measured HBM peak, flops / measured FP64 peak), complex128 operands, real operator values
+    sweep_ms_alone = kernels.get("sweep_lu_gsm", {}).get("ms_per_step")
+    bp_roof = None
+    if sweep_ms_alone:
+        n_loc, r_ = n // world, wl["r"]
+        wbytes = 16.0 if not real else 8.0
+        fl = 1.0 if not real else 0.25                            # real twins: a quarter of the flops
+        bw, p64 = hbm_peak * 1e9, FP64_PEAK_TFLOPS * 1e12
+        t_roof = max(6 * wbytes * n_loc * r_ / bw, 20.0 * n_loc * r_ * r_ * fl / p64)                       # CholeskyQR2 + rotation
+        for a_ in (in_c, in_gamma):
+            nnz_loc = a_.nnz / world
+            t_roof += max((nnz_loc * 12.0 + 4.0 * (n_loc + 1) + 2 * wbytes * n_loc * r_) / bw, (2.0 if real else 4.0) * nnz_loc * r_ / p64)   # SpMM (real operator values)
+            t_roof += max((2 * wbytes * n_loc * r_ + wbytes * r_ * r_) / bw, 8.0 * n_loc * r_ * r_ * fl / p64)     # Q^T (A Q)
+        bp_ms = ms_step - sweep_ms_alone - stage_ms["gather"]
+        bp_roof = {"ms_in_step": bp_ms, "t_roof_ms": t_roof * 1e3, "frac": t_roof * 1e3 / bp_ms if bp_ms > 0 else None,
+                   "note": "whole timed step minus the sweep kernel timed alone; roofline = sum over kernels of max(bytes/HBM, flops/FP64) per GPU"}
+
     if rank == 0:
         sweep_k = kernels.get("sweep_lu_gsm", {})
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -419,6 +453,7 @@ def run_b200(args, wl, rank, world, local_rank):
                            "parallelism": "rows of Q/operators and sweep points block-sharded over %d GPU(s)" % world},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu_baseline,
                 "other_dtype": alt,
+                "basis_plus_projection": bp_roof,
                 "stages": {"basis_plus_projection_ms": stage_ms["basis_plus_projection"], "sweep_ms": stage_ms["sweep"],
                            "gather_ms": stage_ms["gather"],
                            "sweep_kernel_points_per_s_per_gpu": (f_total / world) / (sweep_k["ms_per_step"] * 1e-3) if sweep_k.get("ms_per_step") else None},

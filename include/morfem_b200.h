@@ -70,6 +70,12 @@ int mf_trmm_nn_c128(const mf_c128* A, int64_t lda, int64_t n, int r, const mf_c1
 int mf_equilibrate_c128(mf_c128* G, int64_t ld, int r, double shift, double* d, double* stats, void* stream);
 int mf_potrf_upper_c128(mf_c128* G, int64_t ld, int r, int* info, void* stream);
 int mf_trtri_upper_c128(const mf_c128* R, int64_t ldr, int r, mf_c128* Rinv, int64_t ldi, void* stream);
+/* Fused Cholesky + triangular inverse (one cooperative launch, 32 x 32 blocks, device-wide barriers between the block
+ * steps): G = R^H R in place (R upper, zeros below) and Rinv = R^-1.  info as mf_potrf_upper_c128.  What the
+ * Cholesky-QR passes use above r = 112 (np.linalg.svd replacement, implementation.py:226).  ws: mf_chol_inv_ws_bytes. */
+size_t mf_chol_inv_ws_bytes(int r);
+int mf_chol_inv_upper_c128(mf_c128* G, int64_t ldg, int r, mf_c128* Rinv, int64_t ldi, int* info,
+                           void* ws, size_t ws_bytes, void* stream);
 int mf_scale_cols_c128(mf_c128* X, int64_t ld, int rows, int cols, const double* d, int power, void* stream);
 int mf_scale_rows_c128(mf_c128* X, int64_t ld, int rows, int cols, const double* d, int power, void* stream);
 size_t mf_jacobi_svd_ws_bytes(int r);

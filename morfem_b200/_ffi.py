@@ -31,6 +31,8 @@ SIGNATURES = {
     "mf_equilibrate_c128": (c_int, [c_void_p, c_int64, c_int, c_double, c_void_p, c_void_p, c_void_p]),
     "mf_potrf_upper_c128": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p]),
     "mf_trtri_upper_c128": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int64, c_void_p]),
+    "mf_chol_inv_ws_bytes": (c_size_t, [c_int]),
+    "mf_chol_inv_upper_c128": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int64, c_void_p, c_void_p, c_size_t, c_void_p]),
     "mf_scale_cols_c128": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_int, c_void_p]),
     "mf_scale_rows_c128": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_int, c_void_p]),
     "mf_jacobi_svd_ws_bytes": (c_size_t, [c_int]),

@@ -80,6 +80,43 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" :: "n"(N)); }
 
+// Device-wide barriers of a co-resident (cooperative) grid.
+// (1) shared arrival counter: thread 0 of every CTA adds 1 and polls the counter with a back-off (~2.4 us with 128 CTAs).
+__device__ __forceinline__ void mf_grid_barrier_counter(unsigned* counter, unsigned& epoch, unsigned nblocks) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned target = (epoch + 1u) * nblocks;
+        atomicAdd(counter, 1u);
+        while (*((volatile unsigned*)counter) < target) { __nanosleep(32); }
+        __threadfence();
+    }
+    epoch += 1u;
+    __syncthreads();
+}
+// (2) one flag word per CTA, polled by the first warp of every CTA: no atomics, but every CTA reads every flag, so it
+// only pays for small grids (measured: 128 CTAs polling 128 words turn the flag lines into an L2 hot spot and the
+// barrier gets twice as slow as the counter; with the <= 32 CTAs of the fused Cholesky kernel it is the faster one).
+__device__ __forceinline__ void mf_grid_barrier_flags(unsigned* flags, unsigned& epoch, unsigned nblocks) {
+    __syncthreads();
+    epoch += 1u;
+    if (threadIdx.x < 32) {
+        if (threadIdx.x == 0) {
+            __threadfence();
+            *((volatile unsigned*)(flags + blockIdx.x)) = epoch;
+        }
+        bool done;
+        do {
+            done = true;
+            for (unsigned i = threadIdx.x; i < nblocks; i += 32) done = done && (*((volatile unsigned*)(flags + i)) >= epoch);
+            done = __all_sync(0xffffffffu, done);
+            if (!done) __nanosleep(20);
+        } while (!done);
+        __threadfence();
+    }
+    __syncthreads();
+}
+
 static inline int mf_num_sms() {
     static int sms = 0;
     if (!sms) {

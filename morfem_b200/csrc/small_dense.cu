@@ -172,19 +172,6 @@ __global__ void symmetrize_kernel(const cplx* __restrict__ A, long long lda, int
 // co-residency).  Layout of ws: Xw (r2 x r) | Gacc (r2 x r2) | sig (r2 doubles) | offmax (64 doubles) | counter.
 constexpr int JS_THREADS = 128;
 
-__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& epoch, unsigned nblocks) {
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        const unsigned target = (epoch + 1u) * nblocks;
-        atomicAdd(counter, 1u);
-        while (*((volatile unsigned*)counter) < target) { __nanosleep(32); }
-        __threadfence();
-    }
-    epoch += 1u;
-    __syncthreads();
-}
-
 __device__ __forceinline__ double block_sum4(double& a, double& b, double& c, double& d, double* red) {
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
@@ -213,7 +200,7 @@ jacobi_svd_kernel(const cplx* __restrict__ Xin, long long ld, int r, cplx* __res
         for (int k = tid; k < r2; k += JS_THREADS) Gacc[(long long)row * r2 + k] = cmake(k == row ? 1.0 : 0.0, 0.0);
     }
     if (c == 0) for (int k = tid; k < 64; k += JS_THREADS) offmax[k] = 0.0;
-    grid_barrier(counter, epoch, nblocks);
+    mf_grid_barrier_counter(counter, epoch, nblocks);
 
     int sweep = 0;
     for (; sweep < max_sweeps; ++sweep) {
@@ -253,7 +240,7 @@ jacobi_svd_kernel(const cplx* __restrict__ Xin, long long ld, int r, cplx* __res
                     gq[k] = cadd(cmul(sphc, u), cscale(cs, v));
                 }
             }
-            grid_barrier(counter, epoch, nblocks);
+            mf_grid_barrier_counter(counter, epoch, nblocks);
         }
         const double worst = *((volatile double*)&offmax[sweep & 63]);
         if (!(worst > tol)) { ++sweep; break; }
@@ -265,7 +252,7 @@ jacobi_svd_kernel(const cplx* __restrict__ Xin, long long ld, int r, cplx* __res
         block_sum4(a, z0, z1, z2, red);
         if (tid == 0) sig[row] = sqrt(a);
     }
-    grid_barrier(counter, epoch, nblocks);
+    mf_grid_barrier_counter(counter, epoch, nblocks);
     for (int row = 2 * c; row < 2 * c + 2; ++row) {
         if (row >= r) continue;
         const double s = __ldcg(sig + row);

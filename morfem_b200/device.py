@@ -444,34 +444,37 @@ class BasisInfo:
 _SMALL_NB = 64      # block size: the diagonal blocks run on the single-CTA shared-memory kernels
 
 
-def _potrf_upper(g: torch.Tensor, info: torch.Tensor) -> None:
+_FUSED_CHOL_MIN_R = 113   # from this size on the Cholesky and the inverse run as ONE cooperative kernel (mf_chol_inv_upper_c128)
+
+
+def _potrf_upper(g: torch.Tensor, info: torch.Tensor, want_inverse: bool = False) -> Optional[torch.Tensor]:
     """In-place Cholesky ``G = R^H R`` (R upper) with ``info`` = 0 or the 1-based failing column.  Up to r = 112 one
-    shared-memory kernel; above that a right-looking blocked factorisation whose diagonal blocks use that kernel and
-    whose panel / trailing updates are small DMMA contractions (the one-CTA global-memory kernel needs ~3 ms at r = 256,
-    this ~0.4 ms)."""
+    shared-memory kernel (returns None: invert with ``_trtri_upper``); above that the fused cooperative kernel, which
+    produces ``R^-1`` in the same launch -- returned when ``want_inverse`` (the chain of ~80 small launches a blocked
+    driver over the single-CTA kernels needs at r = 256 took 0.8 ms per Cholesky-QR pass)."""
     lib = _ffi.load()
     r = g.shape[0]
-    if r <= 112:
+    if r < _FUSED_CHOL_MIN_R:
         _ffi.check(lib.mf_potrf_upper_c128(_ptr(g), g.stride(0), r, _ptr(info), _stream()), "mf_potrf_upper_c128")
-        return
-    nblk = (r + _SMALL_NB - 1) // _SMALL_NB
-    infos = torch.zeros(nblk, dtype=torch.int32, device=g.device)
-    for b, j0 in enumerate(range(0, r, _SMALL_NB)):
-        j1 = min(j0 + _SMALL_NB, r)
-        gjj = g[j0:j1, j0:j1]
-        _ffi.check(lib.mf_potrf_upper_c128(_ptr(gjj), g.stride(0), j1 - j0, _ptr(infos[b:]), _stream()), "mf_potrf_upper_c128")
-        if j1 < r:
-            rinv11 = torch.empty((j1 - j0, j1 - j0), dtype=C128, device=g.device)
-            _ffi.check(lib.mf_trtri_upper_c128(_ptr(gjj), g.stride(0), j1 - j0, _ptr(rinv11), rinv11.stride(0), _stream()), "mf_trtri_upper_c128")
-            r12 = gemm_tn(rinv11, g[j0:j1, j1:].contiguous(), conj=True)          # R12 = R11^-H G12
-            g[j0:j1, j1:] = r12
-            g[j1:, j1:] -= gemm_tn(r12, r12, conj=True)                          # G22 -= R12^H R12
-    g.triu_()
-    # first failing block decides (LAPACK info convention, offset by the block start)
-    starts = torch.arange(0, r, _SMALL_NB, dtype=torch.int32, device=g.device)
-    bad = infos != 0
-    first = torch.where(bad, starts + infos, torch.full_like(infos, 2 ** 30)).min()
-    info.copy_(torch.where(bad.any(), first, torch.zeros_like(first)).reshape(1).to(torch.int32))
+        return None
+    rinv = torch.empty((r, r), dtype=C128, device=g.device)
+    nbytes = lib.mf_chol_inv_ws_bytes(r)
+    ws = workspaces.get("chol_inv", nbytes, g.device)
+    _ffi.check(lib.mf_chol_inv_upper_c128(_ptr(g), g.stride(0), r, _ptr(rinv), rinv.stride(0), _ptr(info), _ptr(ws), nbytes, _stream()),
+               "mf_chol_inv_upper_c128")
+    return rinv if want_inverse else None
+
+
+def _unequilibrate(g: torch.Tensor, d: torch.Tensor, rinv_eq: Optional[torch.Tensor]) -> torch.Tensor:
+    """``R = Rtilde D^-1`` in place (undo the equilibration ``G <- D G D``) and ``R^-1 = D Rtilde^-1``: from the fused
+    kernel's inverse when there is one, else by the triangular-inverse kernel."""
+    lib = _ffi.load()
+    r = g.shape[0]
+    _ffi.check(lib.mf_scale_cols_c128(_ptr(g), g.stride(0), r, r, _ptr(d), -1, _stream()), "mf_scale_cols_c128")
+    if rinv_eq is None:
+        return _trtri_upper(g)
+    _ffi.check(lib.mf_scale_rows_c128(_ptr(rinv_eq), rinv_eq.stride(0), r, r, _ptr(d), 1, _stream()), "mf_scale_rows_c128")
+    return rinv_eq
 
 
 def _trtri_upper(rm: torch.Tensor) -> torch.Tensor:
@@ -539,9 +542,7 @@ def _cholesky_qr2_optimistic(s: torch.Tensor, group=None) -> CholQR:
         stats = flags[p, :16].view(torch.float64)
         info = flags[p, 16:20].view(torch.int32)
         _ffi.check(lib.mf_equilibrate_c128(_ptr(g), g.stride(0), r, 0.0, _ptr(d), _ptr(stats), _stream()), "mf_equilibrate_c128")
-        _potrf_upper(g, info)
-        _ffi.check(lib.mf_scale_cols_c128(_ptr(g), g.stride(0), r, r, _ptr(d), -1, _stream()), "mf_scale_cols_c128")
-        rinv = _trtri_upper(g)
+        rinv = _unequilibrate(g, d, _potrf_upper(g, info, want_inverse=True))
         r_tot = g if r_tot is None else gemm_nn(g, r_tot)
         if p == 0:
             x = gemm_nn(x, _like_block(rinv, x), w_upper=True)
@@ -576,7 +577,7 @@ def cholesky_qr(s: torch.Tensor, group=None, max_passes: int = 6, optimistic: bo
         while True:
             gw = g.clone()
             _ffi.check(lib.mf_equilibrate_c128(_ptr(gw), gw.stride(0), r, shift, _ptr(d), _ptr(stats), _stream()), "mf_equilibrate_c128")
-            _potrf_upper(gw, info)
+            rinv_eq = _potrf_upper(gw, info, want_inverse=True)
             host_flags = flags.cpu()
             if int(host_flags[16:20].view(torch.int32)[0]) == 0:
                 break
@@ -587,8 +588,7 @@ def cholesky_qr(s: torch.Tensor, group=None, max_passes: int = 6, optimistic: bo
         shifts.append(shift)
         departure = float(host_flags[:8].view(torch.float64)[0])
         # R = Rtilde D^-1 (undo the equilibration), Rinv = R^-1
-        _ffi.check(lib.mf_scale_cols_c128(_ptr(gw), gw.stride(0), r, r, _ptr(d), -1, _stream()), "mf_scale_cols_c128")
-        rinv = _trtri_upper(gw)
+        rinv = _unequilibrate(gw, d, rinv_eq)
         r_tot = gw if r_tot is None else gemm_nn(gw, r_tot)
         final = (departure < 0.1 and shift == 0.0) or p == max_passes - 1
         if final:

@@ -323,6 +323,44 @@ def test_blocked_cholesky_and_inverse_for_large_r(dv, r):
     assert int(info.item()) == (151 if r > 150 else 101)
 
 
+@pytest.mark.parametrize("r", [1, 5, 31, 32, 33, 64, 100, 150, 256, 300, 512])
+def test_fused_cholesky_inverse_kernel(dv, r):
+    """mf_chol_inv_upper_c128 (one cooperative launch): G = R^H R, R^-1, zeros below the diagonal of both, LAPACK-style
+    info for a matrix that stops being positive definite, ragged last block, strided operands."""
+    from morfem_b200 import _ffi
+    lib = _ffi.load()
+    rng = np.random.default_rng(1000 + r)
+    a = rng.standard_normal((r + 40, r)) + 1j * rng.standard_normal((r + 40, r))
+    g = a.conj().T @ a
+    wide = torch.zeros((r, r + 3), dtype=torch.complex128, device="cuda")          # leading dimension r + 3
+    gd = wide[:, :r]
+    gd.copy_(dv.to_device_c128(g))
+    rinv = torch.full((r, r), 7.0, dtype=torch.complex128, device="cuda")          # stale content must be overwritten
+    info = torch.full((1,), -1, dtype=torch.int32, device="cuda")
+    ws = torch.empty(lib.mf_chol_inv_ws_bytes(r), dtype=torch.uint8, device="cuda")
+    run = lambda m: _ffi.check(lib.mf_chol_inv_upper_c128(dv._ptr(m), m.stride(0), r, dv._ptr(rinv), rinv.stride(0), dv._ptr(info),
+                                                          dv._ptr(ws), ws.numel(), dv._stream()), "mf_chol_inv_upper_c128")
+    run(gd)
+    torch.cuda.synchronize()
+    rr, ri = gd.cpu().numpy(), rinv.cpu().numpy()
+    assert int(info.item()) == 0
+    assert np.all(np.tril(rr, -1) == 0) and np.all(np.tril(ri, -1) == 0)
+    assert np.all(np.diag(rr).real > 0) and np.abs(np.diag(rr).imag).max() == 0
+    assert orc.rel_err(rr.conj().T @ rr, g) < 1e-13
+    ref = np.linalg.cholesky(g).conj().T                                           # LAPACK potrf: the same factor
+    assert orc.rel_err(rr, ref) < 1e-11
+    assert orc.rel_err(ri @ rr, np.eye(r)) < 1e-10
+    first = rr.copy()
+    gd.copy_(dv.to_device_c128(g)); run(gd); torch.cuda.synchronize()
+    assert np.array_equal(gd.cpu().numpy(), first)                                 # deterministic (replicated across ranks)
+    if r >= 5:
+        k = (2 * r) // 3
+        bad = g.copy(); bad[k, :] = 0; bad[:, k] = 0
+        bd = dv.to_device_c128(bad)
+        run(bd)
+        assert int(info.item()) == k + 1
+
+
 def test_e2e_helper_falls_back_when_choleskyqr2_is_not_enough(dv):
     """``model_order_reduction_gsm_from_snapshots`` runs the optimistic CholeskyQR2 and verifies its flags with the result
     download; a nearly collinear snapshot block must take the adaptive (shifted, three-pass) path and still match the oracle."""
