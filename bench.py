@@ -424,6 +424,31 @@ def run_b200(args, wl, rank, world, local_rank):
                                   f"stages 3+4 on {tcpu['points_sampled']} of {f.size} points ({tcpu['sweep_s_per_point'] * 1e6:.0f} + "
                                   f"{tcpu['gsm_s_per_point'] * 1e6:.0f} us/point) scaled linearly; real float64 like the reference"}
 
+    # ---- stages 1+2 alone, device timed (single rank: replayed from their own CUDA graph; N > 1: eager launches)
+    bp_alone_ms = None
+    try:
+        def step12():
+            if use_graph:
+                return path.step_graph(s_dev, want_x=False, skip_sweep=True)
+            return path.step(s_dev, want_x=False, gather=False, optimistic=True, skip_sweep=True)
+        for _ in range(3):
+            step12()
+        barrier()
+        b0_, b1_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        b0_.record()
+        for _ in range(args.steps):
+            step12()
+        b1_.record()
+        barrier()
+        tb = torch.tensor([b0_.elapsed_time(b1_) / args.steps], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tb, op=dist.ReduceOp.MAX)
+        bp_alone_ms = float(tb.item())
+        path._graph = None                                    # the next step_graph call re-captures the full step
+    except Exception as exc:                                  # pragma: no cover - reported, not fatal
+        bp_alone_ms = None
+        print(f"bench: stage-1/2 timing failed: {exc!r}", file=sys.stderr)
+
     # ---- stages 1+2 inside the timed step against their composite roofline: per kernel
     #      max(algorithmic bytes / measured HBM peak, flops / measured FP64 peak), complex128 operands, real operator values
     sweep_ms_alone = kernels.get("sweep_lu_gsm", {}).get("ms_per_step")
@@ -439,8 +464,10 @@ def run_b200(args, wl, rank, world, local_rank):
             t_roof += max((nnz_loc * 12.0 + 4.0 * (n_loc + 1) + 2 * wbytes * n_loc * r_) / bw, (2.0 if real else 4.0) * nnz_loc * r_ / p64)   # SpMM (real operator values)
             t_roof += max((2 * wbytes * n_loc * r_ + wbytes * r_ * r_) / bw, 8.0 * n_loc * r_ * r_ * fl / p64)     # Q^T (A Q)
         bp_ms = ms_step - sweep_ms_alone - stage_ms["gather"]
-        bp_roof = {"ms_in_step": bp_ms, "t_roof_ms": t_roof * 1e3, "frac": t_roof * 1e3 / bp_ms if bp_ms > 0 else None,
-                   "note": "whole timed step minus the sweep kernel timed alone; roofline = sum over kernels of max(bytes/HBM, flops/FP64) per GPU"}
+        bp_roof = {"ms": bp_alone_ms, "t_roof_ms": t_roof * 1e3, "frac": t_roof * 1e3 / bp_alone_ms if bp_alone_ms else None,
+                   "ms_in_step": bp_ms, "frac_in_step": t_roof * 1e3 / bp_ms if bp_ms > 0 else None,
+                   "note": "ms: stages 1+2 timed alone on the device (max over ranks; N=1: their own CUDA graph); ms_in_step: whole timed step minus "
+                           "the sweep kernel timed alone; roofline = sum over kernels of max(bytes/HBM, flops/FP64) per GPU (SURVEY 8d)"}
 
     if rank == 0:
         sweep_k = kernels.get("sweep_lu_gsm", {})

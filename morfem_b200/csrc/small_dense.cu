@@ -2,6 +2,7 @@
 // the B200 replacement of `np.linalg.svd(S, full_matrices=False)[0]`, implementation.py:226/298/210) and the
 // one-off symmetrisation of the reduced operators (implementation.py:528).  All of them touch at most a few
 // MiB that stay in L2; they are latency-, not bandwidth- or flop-bound, so each is a single launch.
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace {
@@ -265,6 +266,145 @@ jacobi_svd_kernel(const cplx* __restrict__ Xin, long long ld, int r, cplx* __res
 }
 
 
+// Block variant of the cooperative kernel (64 < r <= ~900): the device-wide barrier (~2 us) bounds the kernel above,
+// 255 of them per sweep at r = 256.  Here a CTA owns a PAIR OF ROW BLOCKS (B rows each) per tournament round: it stages the
+// 2B rows of X and of the rotation accumulator in shared memory, rotates all B*B cross pairs (B inner rounds of B disjoint
+// pairs, one WARP per pair, CTA barriers only) and writes the rows back -- r2/B - 1 device-wide barriers per sweep instead
+// of r2 - 1.  Pairs inside a block are rotated in round 0 of every sweep (every block is in exactly one pair then), so a
+// sweep still visits every row pair exactly once (a cyclic Jacobi ordering; same convergence test as above).
+constexpr int JB_THREADS = 256;
+template <int B>
+__global__ void __launch_bounds__(JB_THREADS)
+jacobi_svd_block_kernel(const cplx* __restrict__ Xin, long long ld, int r, int r2, cplx* __restrict__ U, long long ldu,
+                        double* __restrict__ sigma, int max_sweeps, double tol, int* sweeps_done, cplx* Xw, cplx* Gacc,
+                        double* sig, double* offmax, unsigned* sync_words) {
+    extern __shared__ __align__(16) cplx jb_sm[];
+    cplx* Xs = jb_sm;                          // 2B x r
+    cplx* Gs = Xs + (size_t)2 * B * r;         // 2B x r2
+    const int nb = r2 / B, c = blockIdx.x, ncta = gridDim.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    unsigned epoch = 0;
+    auto barrier = [&]() {
+        if (ncta <= 32) mf_grid_barrier_flags(sync_words, epoch, ncta);
+        else mf_grid_barrier_counter(sync_words, epoch, ncta);
+    };
+    for (int l = 0; l < 2 * B; ++l) {
+        const int row = c * 2 * B + l;
+        for (int k = tid; k < r; k += JB_THREADS) Xw[(long long)row * r + k] = row < r ? Xin[row * ld + k] : cmake(0.0, 0.0);
+        for (int k = tid; k < r2; k += JB_THREADS) Gacc[(long long)row * r2 + k] = cmake(k == row ? 1.0 : 0.0, 0.0);
+    }
+    if (c == 0) for (int k = tid; k < 64; k += JB_THREADS) offmax[k] = 0.0;
+    barrier();
+
+    int sweep = 0;
+    for (; sweep < max_sweeps; ++sweep) {
+        for (int round = 0; round < nb - 1; ++round) {
+            int P, Q;
+            if (c == 0) { P = nb - 1; Q = round; }
+            else { P = (round + c) % (nb - 1); Q = (round - c + (nb - 1)) % (nb - 1); }
+            if (P > Q) { const int tmp = P; P = Q; Q = tmp; }
+            auto grow = [&](const int l) { return l < B ? P * B + l : Q * B + (l - B); };   // local -> global row (ascending)
+            for (int l = warp; l < 2 * B; l += JB_THREADS / 32) {
+                const cplx* xsrc = Xw + (long long)grow(l) * r;
+                const cplx* gsrc = Gacc + (long long)grow(l) * r2;
+#pragma unroll 8
+                for (int k = lane; k < r; k += 32) Xs[l * r + k] = __ldcg(reinterpret_cast<const double2*>(xsrc + k));
+#pragma unroll 8
+                for (int k = lane; k < r2; k += 32) Gs[l * r2 + k] = __ldcg(reinterpret_cast<const double2*>(gsrc + k));
+            }
+            __syncthreads();
+            double offloc = 0.0;
+            auto rotate_pair = [&](const int la, const int lb) {       // local rows la < lb, one warp
+                cplx* xp = Xs + la * r; cplx* xq = Xs + lb * r;
+                double a = 0.0, b = 0.0, cr = 0.0, ci = 0.0;
+                for (int k = lane; k < r; k += 32) {
+                    const cplx u = xp[k], v = xq[k];
+                    a += cnorm2(u); b += cnorm2(v);
+                    cr += u.x * v.x + u.y * v.y;      // u * conj(v)
+                    ci += u.y * v.x - u.x * v.y;
+                }
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) {
+                    a += __shfl_xor_sync(0xffffffffu, a, off); b += __shfl_xor_sync(0xffffffffu, b, off);
+                    cr += __shfl_xor_sync(0xffffffffu, cr, off); ci += __shfl_xor_sync(0xffffffffu, ci, off);
+                }
+                const double cabs = hypot(cr, ci);
+                const double denom = sqrt(a) * sqrt(b);
+                const double off = denom > 0.0 ? cabs / denom : 0.0;
+                if (off > tol && cabs > 0.0) {
+                    offloc = fmax(offloc, off);
+                    const double zeta = (b - a) / (2.0 * cabs);
+                    const double tt = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+                    const double cs = 1.0 / sqrt(1.0 + tt * tt), sn = cs * tt;
+                    const cplx ph = cmake(cr / cabs, ci / cabs);            // e^{i phi}
+                    const cplx sph = cscale(sn, ph), sphc = cscale(sn, cconj(ph));
+                    for (int k = lane; k < r; k += 32) {
+                        const cplx u = xp[k], v = xq[k];
+                        xp[k] = csub(cscale(cs, u), cmul(sph, v));
+                        xq[k] = cadd(cmul(sphc, u), cscale(cs, v));
+                    }
+                    cplx* gp = Gs + la * r2; cplx* gq = Gs + lb * r2;
+                    for (int k = lane; k < r2; k += 32) {
+                        const cplx u = gp[k], v = gq[k];
+                        gp[k] = csub(cscale(cs, u), cmul(sph, v));
+                        gq[k] = cadd(cmul(sphc, u), cscale(cs, v));
+                    }
+                }
+            };
+            if (round == 0) {                  // pairs inside the two blocks: a (B - 1)-round tournament in each, side by side
+                for (int ir = 0; ir < B - 1; ++ir) {
+                    if (warp < B) {
+                        const int h = warp / (B / 2), sl = warp % (B / 2);
+                        int x, y;
+                        if (sl == 0) { x = B - 1; y = ir; }
+                        else { x = (ir + sl) % (B - 1); y = (ir - sl + (B - 1)) % (B - 1); }
+                        if (x > y) { const int tmp = x; x = y; y = tmp; }
+                        rotate_pair(h * B + x, h * B + y);
+                    }
+                    __syncthreads();
+                }
+            }
+            for (int sft = 0; sft < B; ++sft) {                           // the B * B cross pairs
+                if (warp < B) rotate_pair(warp, B + (warp + sft) % B);
+                __syncthreads();
+            }
+            for (int l = warp; l < 2 * B; l += JB_THREADS / 32) {
+                cplx* xdst = Xw + (long long)grow(l) * r;
+                cplx* gdst = Gacc + (long long)grow(l) * r2;
+                for (int k = lane; k < r; k += 32) xdst[k] = Xs[l * r + k];
+                for (int k = lane; k < r2; k += 32) gdst[k] = Gs[l * r2 + k];
+            }
+            if (lane == 0 && offloc > 0.0) atomicMax((unsigned long long*)&offmax[sweep & 63], (unsigned long long)__double_as_longlong(offloc));
+            barrier();
+        }
+        const double worst = *((volatile double*)&offmax[sweep & 63]);
+        if (!(worst > tol)) { ++sweep; break; }
+    }
+    // singular values = row norms (this CTA: its 2B consecutive rows)
+    for (int l = warp; l < 2 * B; l += JB_THREADS / 32) {
+        const int row = c * 2 * B + l;
+        double a = 0.0;
+        for (int k = lane; k < r; k += 32) a += cnorm2(__ldcg(reinterpret_cast<const double2*>(Xw + (long long)row * r + k)));
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) a += __shfl_xor_sync(0xffffffffu, a, off);
+        if (lane == 0) sig[row] = sqrt(a);
+    }
+    barrier();
+    for (int l = warp; l < 2 * B; l += JB_THREADS / 32) {
+        const int row = c * 2 * B + l;
+        if (row >= r) continue;
+        const double sv = __ldcg(sig + row);
+        int rank = 0;
+        for (int j = lane; j < r; j += 32) { const double sj = __ldcg(sig + j); rank += (sj > sv) || (sj == sv && j < row); }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) rank += __shfl_xor_sync(0xffffffffu, rank, off);
+        if (lane == 0) sigma[rank] = sv;
+        for (int k = lane; k < r; k += 32) U[k * ldu + rank] = cconj(__ldcg(reinterpret_cast<const double2*>(Gacc + (long long)row * r2 + k)));
+    }
+    if (c == 0 && tid == 0 && sweeps_done) *sweeps_done = sweep;
+}
+
+
 // Single-CTA variant for r <= 64: the whole problem (X and the rotation accumulator) lives in shared memory, one WARP
 // per row pair, __syncthreads between tournament rounds instead of a device-wide barrier (~50 ns instead of ~2 us).
 constexpr int JS_SMEM_MAX = 64;
@@ -510,7 +650,7 @@ static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; 
 
 extern "C" size_t mf_jacobi_svd_ws_bytes(int r) {
     if (r <= 0) return 256;
-    size_t r2 = (size_t)((r + 1) & ~1);
+    size_t r2 = (size_t)((r + 15) & ~15);            // the block kernel pads to a multiple of 2B = 16 rows
     return align_up(sizeof(cplx) * r2 * r, 256) + align_up(sizeof(cplx) * r2 * r2, 256) + align_up(sizeof(double) * r2, 256) + 64 * sizeof(double) + 256;
 }
 
@@ -530,6 +670,30 @@ extern "C" int mf_jacobi_svd_c128(mf_c128* X, int64_t ld, int r, mf_c128* U, int
         jacobi_svd_smem_kernel<<<1, (unsigned)(32 * (r2 / 2)), smem, st>>>((const cplx*)X, ld, r, (cplx*)U, ldu, sigma, max_sweeps, tol, sweeps_done);
         MF_CHECK_LAUNCH();
         return 0;
+    }
+    {   // block kernel: 8 rows per block while 16 rows of X and of the accumulator fit in shared memory, else 4
+        const int B = ((size_t)16 * (2 * (size_t)r + 16) * sizeof(cplx) <= 220 * 1024) ? 8 : 4;
+        const size_t r2b = ((size_t)r + 2 * B - 1) / (2 * B) * (2 * B);
+        const size_t smem = sizeof(cplx) * 2 * B * ((size_t)r + r2b);
+        const int grid = (int)(r2b / B / 2);
+        const char* force_old = getenv("MF_JACOBI_PAIR_KERNEL");
+        if (smem <= 220 * 1024 && grid <= mf_num_sms() && !(force_old && atoi(force_old))) {
+            char* base = (char*)ws;
+            cplx* Xw = (cplx*)base; base += align_up(sizeof(cplx) * r2b * r, 256);
+            cplx* Gacc = (cplx*)base; base += align_up(sizeof(cplx) * r2b * r2b, 256);
+            double* sig = (double*)base; base += align_up(sizeof(double) * r2b, 256);
+            double* offmax = (double*)base; base += 64 * sizeof(double);
+            unsigned* sync_words = (unsigned*)base;
+            MF_CHECK_CUDA(cudaMemsetAsync(sync_words, 0, 256, st));
+            const cplx* Xin = (const cplx*)X; long long ldl = ld, ldul = ldu; cplx* Uc = (cplx*)U; int r2i = (int)r2b;
+            void* args[] = {(void*)&Xin, (void*)&ldl, (void*)&r, (void*)&r2i, (void*)&Uc, (void*)&ldul, (void*)&sigma, (void*)&max_sweeps,
+                            (void*)&tol, (void*)&sweeps_done, (void*)&Xw, (void*)&Gacc, (void*)&sig, (void*)&offmax, (void*)&sync_words};
+            const void* kern = B == 8 ? (const void*)jacobi_svd_block_kernel<8> : (const void*)jacobi_svd_block_kernel<4>;
+            MF_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            MF_CHECK_CUDA(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(JB_THREADS), args, smem, st));
+            g_mf_launches.fetch_add(1, std::memory_order_relaxed);
+            return 0;
+        }
     }
     char* base = (char*)ws;
     cplx* Xw = (cplx*)base; base += align_up(sizeof(cplx) * r2 * r, 256);

@@ -191,26 +191,26 @@ class ShardedHotPath:
             e.record()
             ev.append(e)
 
-    def step_graph(self, s_local: torch.Tensor, want_x: bool = False):
+    def step_graph(self, s_local: torch.Tensor, want_x: bool = False, skip_sweep: bool = False):
         """``step`` replayed from a CUDA graph (single rank): the whole launch sequence -- optimistic CholeskyQR2 (two
         passes, success flags kept on the device), SpMMs, contractions, SVD rotation on its side stream, sweep -- is
         captured once per snapshot-block shape and replayed with one launch, which removes the host launch gaps between
         the ~45 short kernels of a step.  Call ``verify()`` before trusting the results: if a Cholesky broke down or the
         block needed a third pass it re-runs the adaptive ``step``.  Outputs are static tensors overwritten by the next
-        replay."""
+        replay.  ``skip_sweep`` captures stages 1 + 2 only (bench.py times the basis + projection stage with it)."""
         if self.world > 1:
             raise RuntimeError("step_graph is single-rank; use step() under torchrun")
-        key = (tuple(s_local.shape), s_local.dtype, bool(want_x))
+        key = (tuple(s_local.shape), s_local.dtype, bool(want_x), bool(skip_sweep))
         if self._graph is None or self._graph["key"] != key:
             static_s = s_local.clone()
             for _ in range(2):                                   # warm-up: workspaces, function attributes, side stream
-                self.step(static_s, want_x=want_x, gather=False, optimistic=True)
+                self.step(static_s, want_x=want_x, gather=False, optimistic=True, skip_sweep=skip_sweep)
             torch.cuda.synchronize()
             from . import _ffi
             graph = torch.cuda.CUDAGraph()
             launches0 = _ffi.launch_count()
             with torch.cuda.graph(graph):
-                out = self.step(static_s, want_x=want_x, gather=False, optimistic=True)
+                out = self.step(static_s, want_x=want_x, gather=False, optimistic=True, skip_sweep=skip_sweep)
             self.launches_per_graph = _ffi.launch_count() - launches0     # kernels of this library inside one replay
             flags_host = torch.empty((2, 32), dtype=torch.uint8).pin_memory()
             self._graph = {"key": key, "graph": graph, "s": static_s, "out": out, "flags_host": flags_host, "want_x": want_x}
@@ -246,7 +246,7 @@ class ShardedHotPath:
             return None
         return self.step(gr["s"], want_x=gr["want_x"], gather=False)
 
-    def step(self, s_local: torch.Tensor, want_x: bool = False, gather: bool = True, optimistic: bool = False):
+    def step(self, s_local: torch.Tensor, want_x: bool = False, gather: bool = True, optimistic: bool = False, skip_sweep: bool = False):
         """One pass of the hot path.  Returns (gsm_all or gsm_local, q_local, (a0_r, a1_r, a2_r, b_r), sweep result)
         (plus the BasisInfo when ``optimistic``: its ``flags`` still have to be verified, see ``step_graph``)."""
         dv = self.dv
@@ -284,6 +284,9 @@ class ShardedHotPath:
         sym = [None if o is None else dv.symmetrize(o) for o in reduced]
         c0, c1, c2, cb, zs = self.coeffs
         self._mark(ev)
+        if skip_sweep:                       # stages 1 + 2 only (timing of the basis + projection stage)
+            out = (None, q, (reduced[0], reduced[1], reduced[2], b_r), None)
+            return out + (info,) if optimistic else out
         res = dv.sweep(sym[0], sym[1], sym[2], b_r, c0, c1, c2, cb, zs, want_x=want_x, want_gsm=True)
         self._mark(ev)
         gsm = gather_points(res.gsm, self.f_total, group) if (gather and self.world > 1) else res.gsm
