@@ -127,31 +127,44 @@ class _DeviceOperators:
     def __init__(self, md: ModelDefinition, side_stream: bool = False, group_for_r: Optional[int] = None):
         """``side_stream=True`` queues the uploads (and, with ``group_for_r``, the row grouping) on a separate CUDA stream so
         that they overlap with whatever the caller runs on the current stream in the meantime (the Cholesky-QR passes only
-        need the snapshot block); the first projection waits for them."""
+        need the snapshot block).  Every operator gets its own ready event: the projection of the first operator runs while
+        the next one is still crossing PCIe.  ``group_for_r=None`` keeps the plain CSR operands (building the row-grouped
+        form costs about one SpMM, so it only pays when the operators stay on the device for many calls)."""
         from . import device as dv
         import torch
         self.dv = dv
         self.dev = dv.require_cuda()
         self.ops = [md.a0, md.a1, md.a2]
         self.zero = [_is_zero_operator(a) for a in self.ops]
-        self._ready = None
+        self.grouped = group_for_r is not None
+        self._ready = {}
         stream = dv.upload_stream(self.dev) if side_stream else torch.cuda.current_stream()
-        with torch.cuda.stream(stream):
-            # CSR of a^T == CSC arrays of a: what `q_t @ a` multiplies by (implementation.py:181-183)
-            self.at = [None if z else dv.csr_of_transpose(a, self.dev, group_for_r=group_for_r) for a, z in zip(self.ops, self.zero)]
-            self.b = dv.csc_to_device(md.b, self.dev)
+
+        def mark(key):
             if side_stream:
-                self._ready = torch.cuda.Event()
-                self._ready.record(stream)
+                ev = torch.cuda.Event()
+                ev.record(stream)
+                self._ready[key] = ev
+
+        with torch.cuda.stream(stream):
+            self.b = dv.csc_to_device(md.b, self.dev)        # tiny, first
+            mark("b")
+            # CSR of a^T == CSC arrays of a: what `q_t @ a` multiplies by (implementation.py:181-183)
+            self.at = []
+            for i, (a, z) in enumerate(zip(self.ops, self.zero)):
+                self.at.append(None if z else dv.csr_of_transpose(a, self.dev, group_for_r=group_for_r))
+                if not z:
+                    mark(i)
         self._a = [None, None, None]   # CSR of a itself, built lazily for the estimator (a_i @ q)
         self.b_host = csc_array(md.b)
 
-    def wait_ready(self):
-        """Make the current stream wait for side-stream uploads (no-op otherwise)."""
-        if self._ready is not None:
-            import torch
-            torch.cuda.current_stream().wait_event(self._ready)
-            self._ready = None
+    def wait_ready(self, key=None):
+        """Make the current stream wait for the side-stream upload of one operand (``key`` = operator index or "b") or of
+        all of them (no-op once waited for, or without a side stream)."""
+        import torch
+        keys = list(self._ready) if key is None else ([key] if key in self._ready else [])
+        for k in keys:
+            torch.cuda.current_stream().wait_event(self._ready.pop(k))
 
     def a_csr(self, i):
         if self._a[i] is None and not self.zero[i]:
@@ -162,11 +175,16 @@ class _DeviceOperators:
     def project_block(self, x):
         """``x^T (a_i x)`` for every operator and ``x^T b`` -- the callback of ``device.basis_and_projection``."""
         dv = self.dv
-        self.wait_ready()
-        for at in self.at:
-            if at is not None:
+        g_list = []
+        for i, (at, z) in enumerate(zip(self.at, self.zero)):
+            if z:
+                g_list.append(None)
+                continue
+            self.wait_ready(i)
+            if self.grouped:
                 dv.group_rows(at, x.shape[1])
-        g_list = [None if z else dv.gemm_tn(dv.spmm(at, x), x, conj=False) for at, z in zip(self.at, self.zero)]
+            g_list.append(dv.gemm_tn(dv.spmm(at, x), x, conj=False))
+        self.wait_ready("b")
         return g_list, dv.project_rhs(self.b, x, 0, conj=False)
 
     def project(self, q):

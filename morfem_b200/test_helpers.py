@@ -147,6 +147,8 @@ def model_order_reduction_gsm_from_snapshots(frequency_points, snapshots, in_c, 
     # stream) overlap with them
     s_dev = dv.real_or_complex_to_device(snapshots, widen=widen)
     r = s_dev.shape[1]
+    # copies queued on two streams share the PCIe link: the operator uploads start only when the snapshot block has arrived
+    dv.upload_stream(s_dev.device).wait_stream(torch.cuda.current_stream())
     if operators_resident:
         key = (id(in_c), id(in_gamma), id(in_b))
         hit = _resident_ops.get(key)
@@ -155,7 +157,7 @@ def model_order_reduction_gsm_from_snapshots(frequency_points, snapshots, in_c, 
             hit = _resident_ops[key] = (impl._DeviceOperators(md, side_stream=True, group_for_r=r), (in_c, in_gamma, in_b))
         ops = hit[0]
     else:
-        ops = impl._DeviceOperators(md, side_stream=True, group_for_r=r)
+        ops = impl._DeviceOperators(md, side_stream=True)          # one-shot: plain CSR operands, no grouping pass
     # optimistic CholeskyQR2 (no device->host read until the results are fetched); verified below, adaptive path on failure
     optimistic = impl.TRUNCATION_TOL == 0.0
     _, (a0_r, a1_r, a2_r), b_r, info = dv.basis_and_projection(s_dev, ops.project_block, truncation_tol=impl.TRUNCATION_TOL,
