@@ -665,7 +665,8 @@ def upload_stream(dev) -> "torch.cuda.Stream":
 
 
 
-def basis_and_projection(s: torch.Tensor, project_block, group=None, truncation_tol: float = 0.0, optimistic: bool = False):
+def basis_and_projection(s: torch.Tensor, project_block, group=None, truncation_tol: float = 0.0, optimistic: bool = False,
+                         defer_q: bool = False, want_q: bool = True):
     """Stages 1 + 2 with the small-matrix work taken off the critical path.
 
     ``project_block(x)`` must return ``(g_list, bt)``: the (all-reduced) r x r products ``x^T (A_i x)`` for every
@@ -673,6 +674,11 @@ def basis_and_projection(s: torch.Tensor, project_block, group=None, truncation_
     basis is ``q = x w`` with a small r x r' matrix ``w`` (inverse triangular factor times the SVD rotation),
     ``q^T A q = w^T (x^T A x) w``: the SpMMs and the long contractions do not wait for the Jacobi SVD, which runs
     (with ``q = x w`` itself) on a side stream concurrently with them.  Returns ``(q, [a_i_r], b_r, BasisInfo)``.
+
+    The reduced operators only need ``w``: the current stream waits for the rotation, not for the tall product ``q = x w``,
+    which keeps running on the side stream under the small ``w^T (.) w`` products.  With ``defer_q`` the current stream is
+    not joined with it at all: ``info.q_ready`` is the event to wait for before ``q`` is used (or the step ends) -- the
+    caller launches the sweep first.  ``want_q=False`` skips ``q`` (callers that only need the reduced model).
     """
     dev = s.device
     cq = cholesky_qr(s, group=group, optimistic=optimistic)
@@ -687,10 +693,12 @@ def basis_and_projection(s: torch.Tensor, project_block, group=None, truncation_
     with torch.cuda.stream(side):
         w, info = basis_rotation(cq, truncation_tol)
         w = _like_block(w, cq.x)
-        q = gemm_nn(cq.x, w)
+        ev_w = torch.cuda.Event()
+        ev_w.record(side)
+        q = gemm_nn(cq.x, w) if want_q else None
         ev1 = torch.cuda.Event()
         ev1.record(side)
-    main.wait_event(ev1)
+    main.wait_event(ev_w)
     if not torch.cuda.is_current_stream_capturing():
         for t in (w, q, info._sigma, info._sweeps):
             if isinstance(t, torch.Tensor):
@@ -699,6 +707,11 @@ def basis_and_projection(s: torch.Tensor, project_block, group=None, truncation_
     reduced = [None if g is None else gemm_nn(gemm_tn(w, g, conj=False), w) for g in g_list]
     b_r = gemm_tn(w, bt, conj=False)
     info.flags = cq.flags            # None unless optimistic: the caller verifies with flags_ok(flags.cpu())
+    info.q_ready = None
+    if defer_q and want_q:
+        info.q_ready = ev1           # the caller joins: current_stream().wait_event(info.q_ready)
+    else:
+        main.wait_event(ev1)
     return q, reduced, b_r, info
 
 

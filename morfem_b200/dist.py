@@ -280,14 +280,24 @@ class ShardedHotPath:
             allreduce_sum_(flat, group)
             return g_list, bt
 
-        q, reduced, b_r, info = dv.basis_and_projection(s_local, project_block, group=group, optimistic=optimistic)
+        # the sweep only needs the reduced model: it is launched before the stream is joined with the tall product q = x w
+        q, reduced, b_r, info = dv.basis_and_projection(s_local, project_block, group=group, optimistic=optimistic, defer_q=True)
         sym = [None if o is None else dv.symmetrize(o) for o in reduced]
         c0, c1, c2, cb, zs = self.coeffs
-        self._mark(ev)
+
+        def join_q():
+            if info.q_ready is not None:
+                torch.cuda.current_stream().wait_event(info.q_ready)
+                info.q_ready = None
+
         if skip_sweep:                       # stages 1 + 2 only (timing of the basis + projection stage)
+            join_q()
+            self._mark(ev)
             out = (None, q, (reduced[0], reduced[1], reduced[2], b_r), None)
             return out + (info,) if optimistic else out
+        self._mark(ev)
         res = dv.sweep(sym[0], sym[1], sym[2], b_r, c0, c1, c2, cb, zs, want_x=want_x, want_gsm=True)
+        join_q()
         self._mark(ev)
         gsm = gather_points(res.gsm, self.f_total, group) if (gather and self.world > 1) else res.gsm
         self._mark(ev)

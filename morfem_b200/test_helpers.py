@@ -160,12 +160,13 @@ def model_order_reduction_gsm_from_snapshots(frequency_points, snapshots, in_c, 
         ops = impl._DeviceOperators(md, side_stream=True)          # one-shot: plain CSR operands, no grouping pass
     # optimistic CholeskyQR2 (no device->host read until the results are fetched); verified below, adaptive path on failure
     optimistic = impl.TRUNCATION_TOL == 0.0
+    # (only the S-parameters leave this call: the tall product q = x w is not formed)
     _, (a0_r, a1_r, a2_r), b_r, info = dv.basis_and_projection(s_dev, ops.project_block, truncation_tol=impl.TRUNCATION_TOL,
-                                                               optimistic=optimistic)
+                                                               optimistic=optimistic, want_q=False)
     res = impl._sweep_device(frequency_points, [a0_r, a1_r, a2_r], b_r, md.t_a0, md.t_a1, md.t_a2, md.t_b, want_x=False, want_gsm=True)
     gsm = dv.download(res.gsm, pinned_out)
     if optimistic and not dv.flags_ok(info.flags.cpu()):
-        _, (a0_r, a1_r, a2_r), b_r, info = dv.basis_and_projection(s_dev, ops.project_block, truncation_tol=impl.TRUNCATION_TOL)
+        _, (a0_r, a1_r, a2_r), b_r, info = dv.basis_and_projection(s_dev, ops.project_block, truncation_tol=impl.TRUNCATION_TOL, want_q=False)
         res = impl._sweep_device(frequency_points, [a0_r, a1_r, a2_r], b_r, md.t_a0, md.t_a1, md.t_a2, md.t_b, want_x=False, want_gsm=True)
         gsm = dv.download(res.gsm, pinned_out)
     impl._warn_singular(dv.download(res.info))
