@@ -101,6 +101,23 @@ def reduced_sweep(domain: Sequence[float], a0, a1, a2, b,
     return x
 
 
+def full_order_sweep(domain: Sequence[float], a0, a1, a2, b,
+                     t_a0: Callable, t_a1: Callable, t_a2: Callable, t_b: Callable) -> np.ndarray:
+    """The full-order yardstick / snapshot solves: implementation.py:189-194 with the SPARSE branch of ``solve_fem_point``
+    (:472-475, ``splu(a).solve(b)`` of the symmetrised system matrix :526-528 and the densified right-hand side :531-533).
+    Outside the hot path (it stays scipy SuperLU in the product too); the tests use it for the BASELINE config-4 study."""
+    from scipy.sparse import csc_matrix
+    from scipy.sparse.linalg import splu
+    domain = np.asarray(domain)
+    x = np.zeros((domain.size, b.shape[0], b.shape[1]))
+    for i in range(domain.size):
+        t = domain[i]
+        a = t_a0(t) * a0 + t_a1(t) * a1 + t_a2(t) * a2
+        a = csc_matrix((a + a.T) / 2)
+        x[i] = splu(a).solve(np.asarray((t_b(t) * b).todense()))
+    return x
+
+
 # ----------------------------------------------------------------------------------------------- stage 4
 def b_coefficient(t: float) -> float:
     """test_helpers.py:70-72; ``math.sqrt`` raises ValueError below the TE cutoff (~2.605 GHz)."""

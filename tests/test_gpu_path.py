@@ -378,3 +378,38 @@ def test_e2e_helper_falls_back_when_choleskyqr2_is_not_enough(dv):
     cond = np.array([np.linalg.cond(orc.system_matrix(1.0, t, t ** 2, a0, a1, a2)) for t in f])
     err = np.linalg.norm((gsm - s_ref).reshape(f.size, -1), axis=1) / np.linalg.norm(s_ref.reshape(f.size, -1), axis=1)
     assert np.all(err < np.maximum(1e-7, 1e3 * np.finfo(float).eps * cond)), err.max()
+
+
+def test_basis_size_study_config4(dv):
+    """BASELINE config 4 (the reference's speed_and_error_of_no_points_in_q experiment through the current API):
+    S-parameter error of the reduced sweep against the full-order sweep as the number of equally spaced snapshot points
+    grows.  The GPU path must reproduce the CPU restatement of the same experiment size by size and converge like it."""
+    import importlib.util, os
+    from morfem_b200 import synthetic
+    spec = importlib.util.spec_from_file_location("basis_size_sweep", os.path.join(os.path.dirname(__file__), "..", "examples", "basis_size_sweep.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    ct, tt = synthetic.waveguide_operators(6, 4, 40)
+    n = ct.shape[0]
+    in_c, in_gamma, in_b = synthetic.driver_scaled(ct, tt, synthetic.port_matrix(n, 2, 19))
+    f = np.linspace(3e9, 5e9, 41)
+    sizes = [2, 3, 4, 5, 6]          # cond(snapshot block) 1e2 .. 1e9: the last sizes take the shifted Cholesky-QR path
+    rows = mod.basis_size_study(f, in_c, in_gamma, in_b, sizes)
+    assert [r["snapshot_points"] for r in rows] == sizes and [r["r"] for r in rows] == [2 * k for k in sizes]
+    # the oracle's version of the experiment: same snapshots -> svd basis -> projection -> sweep -> S-parameters (all CPU)
+    from scipy.sparse import csc_array
+    full = orc.full_order_sweep(f, in_c, csc_array(in_c.shape), in_gamma, in_b, lambda t: 1.0, lambda t: t, lambda t: t ** 2, orc.b_coefficient)
+    ref_gsm = orc.scattering_sweep(f, full, in_b.toarray())
+    errs_cpu = []
+    for k in sizes:
+        idx = np.linspace(0, f.size - 1, k, dtype=int)
+        snaps = np.concatenate([full[i] for i in idx], axis=1)
+        q = orc.orthonormal_basis(snaps)
+        a0_r, a1_r, a2_r, b_r = orc.galerkin_projection(q, in_c, csc_array(in_c.shape), in_gamma, in_b)
+        x = orc.reduced_sweep(f, a0_r, a1_r, a2_r, b_r, lambda t: 1.0, lambda t: t, lambda t: t ** 2, orc.b_coefficient)
+        gsm = orc.scattering_sweep(f, x, b_r)
+        errs_cpu.append(np.mean([np.linalg.norm(gsm[i] - ref_gsm[i]) for i in range(f.size)]))
+    errs_gpu = [r["error_mean"] for r in rows]
+    for eg, ec in zip(errs_gpu, errs_cpu):
+        assert abs(eg - ec) <= 0.05 * ec + 5e-10, (errs_gpu, errs_cpu)      # same error curve (7e-6, 2e-8, 7e-11, ... on the CPU)
+    assert errs_gpu[0] > errs_gpu[1] > errs_gpu[2] and errs_gpu[-1] < 1e-9
