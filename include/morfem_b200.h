@@ -90,6 +90,14 @@ int mf_jacobi_svd_c128(mf_c128* X, int64_t ld, int r, mf_c128* U, int64_t ldu, d
  * stay global (they index rows of Q). */
 int mf_spmm_csr_c128(const int32_t* rowptr, const int32_t* colidx, const void* vals, int val_is_real,
                      int64_t nrows, const mf_c128* Q, int64_t ldq, int r, mf_c128* Y, int64_t ldy, void* stream);
+/* Two operators that share ONE sparsity pattern (the reference's Ct and Tt: stiffness and mass matrix of the same mesh,
+ * projected back to back at implementation.py:181-183): Y0 = A0 Q and Y1 = A1 Q in one pass over the pattern -- every Q row is
+ * loaded once for both.  vals0 / vals1 follow the same val_is_real. */
+int mf_spmm_csr2_c128(const int32_t* rowptr, const int32_t* colidx, const void* vals0, const void* vals1, int val_is_real,
+                      int64_t nrows, const mf_c128* Q, int64_t ldq, int r, mf_c128* Y0, int64_t ldy0, mf_c128* Y1, int64_t ldy1,
+                      void* stream);
+int mf_spmm_csr2_f64(const int32_t* rowptr, const int32_t* colidx, const double* vals0, const double* vals1, int64_t nrows,
+                     const double* Q, int64_t ldq, int r, double* Y0, int64_t ldy0, double* Y1, int64_t ldy1, void* stream);
 
 /* Row-grouped form of the same product for real operators with sorted column indices (the FEM operators of this path):
  * G = mf_spmm_group_size(r) consecutive rows are handled by one warp over the UNION of their columns, so that each

@@ -40,6 +40,10 @@ SIGNATURES = {
                                    c_void_p, c_size_t, c_void_p]),
     "mf_spmm_csr_c128": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int64, c_void_p, c_int64, c_int, c_void_p, c_int64,
                                  c_void_p]),
+    "mf_spmm_csr2_c128": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_void_p, c_int64, c_int, c_void_p, c_int64,
+                                  c_void_p, c_int64, c_void_p]),
+    "mf_spmm_csr2_f64": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int, c_void_p, c_int64,
+                                 c_void_p, c_int64, c_void_p]),
     "mf_spmm_group_size": (c_int, [c_int]),
     "mf_spmm_group_count": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p]),
     "mf_spmm_group_fill": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),

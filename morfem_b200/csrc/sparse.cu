@@ -74,6 +74,93 @@ int spmm_dispatch(const int* rowptr, const int* colidx, const void* vals, long l
     return 0;
 }
 
+// Two operators with ONE sparsity pattern (stiffness and mass matrix of the same mesh -- the reference's Ct and Tt): every
+// Q row is pulled through L1 once and feeds both accumulator sets, which halves the register-fill traffic that bounds the
+// single-operator kernel.  Y0 = A0 Q, Y1 = A1 Q.
+template <int CPL, bool REAL>
+__global__ void __launch_bounds__(256)
+spmm_csr2_kernel(const int* __restrict__ rowptr, const int* __restrict__ colidx, const void* __restrict__ vals0_v,
+                 const void* __restrict__ vals1_v, long long nrows, const cplx* __restrict__ Q, long long ldq, int r,
+                 cplx* __restrict__ Y0, long long ldy0, cplx* __restrict__ Y1, long long ldy1) {
+    const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (row >= nrows) return;
+    const int s = rowptr[row], e = rowptr[row + 1];
+    cplx acc0[CPL], acc1[CPL];
+#pragma unroll
+    for (int c = 0; c < CPL; ++c) { acc0[c] = cmake(0.0, 0.0); acc1[c] = cmake(0.0, 0.0); }
+    for (int base = s; base < e; base += 32) {
+        const int cnt = min(32, e - base);
+        int my_col = 0; cplx my_v0 = cmake(0.0, 0.0), my_v1 = cmake(0.0, 0.0);
+        if (lane < cnt) {
+            my_col = colidx[base + lane];
+            if (REAL) {
+                my_v0 = cmake(reinterpret_cast<const double*>(vals0_v)[base + lane], 0.0);
+                my_v1 = cmake(reinterpret_cast<const double*>(vals1_v)[base + lane], 0.0);
+            } else {
+                my_v0 = reinterpret_cast<const cplx*>(vals0_v)[base + lane];
+                my_v1 = reinterpret_cast<const cplx*>(vals1_v)[base + lane];
+            }
+        }
+#pragma unroll 2
+        for (int k = 0; k < cnt; ++k) {
+            const int col = __shfl_sync(0xffffffffu, my_col, k);
+            cplx v0, v1;
+            v0.x = __shfl_sync(0xffffffffu, my_v0.x, k); v1.x = __shfl_sync(0xffffffffu, my_v1.x, k);
+            if (!REAL) { v0.y = __shfl_sync(0xffffffffu, my_v0.y, k); v1.y = __shfl_sync(0xffffffffu, my_v1.y, k); }
+            else { v0.y = 0.0; v1.y = 0.0; }
+            const cplx* q = Q + (long long)col * ldq;
+            cplx qv[CPL];
+#pragma unroll
+            for (int c = 0; c < CPL; ++c) { const int idx = lane + 32 * c; qv[c] = idx < r ? ldg_q(q + idx) : cmake(0.0, 0.0); }
+#pragma unroll
+            for (int c = 0; c < CPL; ++c) {
+                if (REAL) {
+                    acc0[c].x = fma(v0.x, qv[c].x, acc0[c].x); acc0[c].y = fma(v0.x, qv[c].y, acc0[c].y);
+                    acc1[c].x = fma(v1.x, qv[c].x, acc1[c].x); acc1[c].y = fma(v1.x, qv[c].y, acc1[c].y);
+                } else { cfma(acc0[c], v0, qv[c]); cfma(acc1[c], v1, qv[c]); }
+            }
+        }
+    }
+    cplx* y0 = Y0 + row * ldy0; cplx* y1 = Y1 + row * ldy1;
+#pragma unroll
+    for (int c = 0; c < CPL; ++c) { const int idx = lane + 32 * c; if (idx < r) { y0[idx] = acc0[c]; y1[idx] = acc1[c]; } }
+}
+
+// real float64 twin of the two-operator kernel
+template <int CPL>
+__global__ void __launch_bounds__(256)
+spmm_csr2_f64_kernel(const int* __restrict__ rowptr, const int* __restrict__ colidx, const double* __restrict__ vals0,
+                     const double* __restrict__ vals1, long long nrows, const double* __restrict__ Q, long long ldq, int r,
+                     double* __restrict__ Y0, long long ldy0, double* __restrict__ Y1, long long ldy1) {
+    const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (row >= nrows) return;
+    const int s = rowptr[row], e = rowptr[row + 1];
+    double acc0[CPL], acc1[CPL];
+#pragma unroll
+    for (int c = 0; c < CPL; ++c) { acc0[c] = 0.0; acc1[c] = 0.0; }
+    for (int base = s; base < e; base += 32) {
+        const int cnt = min(32, e - base);
+        int my_col = 0; double my_v0 = 0.0, my_v1 = 0.0;
+        if (lane < cnt) { my_col = colidx[base + lane]; my_v0 = vals0[base + lane]; my_v1 = vals1[base + lane]; }
+#pragma unroll 4
+        for (int k = 0; k < cnt; ++k) {
+            const int col = __shfl_sync(0xffffffffu, my_col, k);
+            const double v0 = __shfl_sync(0xffffffffu, my_v0, k), v1 = __shfl_sync(0xffffffffu, my_v1, k);
+            const double* q = Q + (long long)col * ldq;
+#pragma unroll
+            for (int c = 0; c < CPL; ++c) {
+                const int idx = lane + 32 * c;
+                if (idx < r) { const double qv = __ldg(q + idx); acc0[c] = fma(v0, qv, acc0[c]); acc1[c] = fma(v1, qv, acc1[c]); }
+            }
+        }
+    }
+    double* y0 = Y0 + row * ldy0; double* y1 = Y1 + row * ldy1;
+#pragma unroll
+    for (int c = 0; c < CPL; ++c) { const int idx = lane + 32 * c; if (idx < r) { y0[idx] = acc0[c]; y1[idx] = acc1[c]; } }
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // Row-grouped SpMM.  ncu shows the CSR kernel bound by the L1/TEX data path, not by HBM: every non-zero pulls a whole Q
 // row (16 r bytes) into registers, 24 times per matrix row for the FEM stencils of this path.  Neighbouring rows of a
@@ -472,6 +559,53 @@ extern "C" int mf_project_rhs_f64(const int32_t* colptr, const int32_t* rowidx, 
     if (r <= 0) MF_FAIL_ARG(7, "r <= 0");
     if (!Br || ldb < m) MF_FAIL_ARG(10, "Br is NULL or ldb < m");
     project_rhs_f64_kernel<<<m, 256, 0, (cudaStream_t)stream>>>(colptr, rowidx, vals, Q, ldq, r, row0, nlocal, Br, ldb);
+    MF_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int mf_spmm_csr2_c128(const int32_t* rowptr, const int32_t* colidx, const void* vals0, const void* vals1, int val_is_real,
+                                 int64_t nrows, const mf_c128* Q, int64_t ldq, int r, mf_c128* Y0, int64_t ldy0, mf_c128* Y1, int64_t ldy1,
+                                 void* stream) {
+    if (!rowptr) MF_FAIL_ARG(1, "rowptr is NULL");
+    if (!colidx) MF_FAIL_ARG(2, "colidx is NULL");
+    if (!vals0) MF_FAIL_ARG(3, "vals0 is NULL");
+    if (!vals1) MF_FAIL_ARG(4, "vals1 is NULL");
+    if (nrows < 0) MF_FAIL_ARG(6, "nrows < 0");
+    if (!Q || ldq < r) MF_FAIL_ARG(7, "Q is NULL or ldq < r");
+    if (r <= 0 || r > 512) MF_FAIL_ARG(9, "need 0 < r <= 512");
+    if (!Y0 || ldy0 < r) MF_FAIL_ARG(10, "Y0 is NULL or ldy0 < r");
+    if (!Y1 || ldy1 < r) MF_FAIL_ARG(12, "Y1 is NULL or ldy1 < r");
+    if (nrows == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long blocks = (nrows * 32 + 255) / 256;
+    if (blocks > 0x7fffffffLL) MF_FAIL_ARG(6, "nrows too large for one launch");
+#define SPMM2(C, RL) spmm_csr2_kernel<C, RL><<<(unsigned)blocks, 256, 0, st>>>(rowptr, colidx, vals0, vals1, nrows, (const cplx*)Q, ldq, r, (cplx*)Y0, ldy0, (cplx*)Y1, ldy1)
+#define SPMM2_R(RL) do { if (r <= 32) SPMM2(1, RL); else if (r <= 64) SPMM2(2, RL); else if (r <= 128) SPMM2(4, RL); else if (r <= 256) SPMM2(8, RL); else SPMM2(16, RL); } while (0)
+    if (val_is_real) SPMM2_R(true); else SPMM2_R(false);
+#undef SPMM2_R
+#undef SPMM2
+    MF_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int mf_spmm_csr2_f64(const int32_t* rowptr, const int32_t* colidx, const double* vals0, const double* vals1, int64_t nrows,
+                                const double* Q, int64_t ldq, int r, double* Y0, int64_t ldy0, double* Y1, int64_t ldy1, void* stream) {
+    if (!rowptr) MF_FAIL_ARG(1, "rowptr is NULL");
+    if (!colidx) MF_FAIL_ARG(2, "colidx is NULL");
+    if (!vals0) MF_FAIL_ARG(3, "vals0 is NULL");
+    if (!vals1) MF_FAIL_ARG(4, "vals1 is NULL");
+    if (nrows < 0) MF_FAIL_ARG(5, "nrows < 0");
+    if (!Q || ldq < r) MF_FAIL_ARG(6, "Q is NULL or ldq < r");
+    if (r <= 0 || r > 512) MF_FAIL_ARG(8, "need 0 < r <= 512");
+    if (!Y0 || ldy0 < r) MF_FAIL_ARG(9, "Y0 is NULL or ldy0 < r");
+    if (!Y1 || ldy1 < r) MF_FAIL_ARG(11, "Y1 is NULL or ldy1 < r");
+    if (nrows == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long blocks = (nrows * 32 + 255) / 256;
+    if (blocks > 0x7fffffffLL) MF_FAIL_ARG(5, "nrows too large for one launch");
+#define RSPMM2(C) spmm_csr2_f64_kernel<C><<<(unsigned)blocks, 256, 0, st>>>(rowptr, colidx, vals0, vals1, nrows, Q, ldq, r, Y0, ldy0, Y1, ldy1)
+    if (r <= 32) RSPMM2(1); else if (r <= 64) RSPMM2(2); else if (r <= 128) RSPMM2(4); else if (r <= 256) RSPMM2(8); else RSPMM2(16);
+#undef RSPMM2
     MF_CHECK_LAUNCH();
     return 0;
 }

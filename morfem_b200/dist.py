@@ -176,6 +176,13 @@ class ShardedHotPath:
             csr = dv.csr_of_transpose(a, self.dev, row_range=(self.row0, self.row1), col_offset=plan.win0)   # window-relative columns
             self.ops.append(csr)
             self.plans.append(plan)
+        # operators with one sparsity pattern (Ct and Tt of a FEM model) are multiplied in one pass (device.spmm2)
+        live = [i for i, c in enumerate(self.ops) if c is not None]
+        self.pair = None
+        if len(live) == 2 and self.plans[live[0]].win0 == self.plans[live[1]].win0 and self.plans[live[0]].win1 == self.plans[live[1]].win1:
+            i0, i1 = live
+            if dv.mark_same_pattern(self.ops[i0], self.ops[i1], operators[i0], operators[i1], row_range=(self.row0, self.row1)):
+                self.pair = (i0, i1)
         self.b = dv.csc_to_device(b, self.dev)
         self.coeffs = [dv.upload(np.ascontiguousarray(c[self.f0:self.f1], dtype=np.float64), self.dev) for c in coeffs_global]
         self._win = None
@@ -259,9 +266,21 @@ class ShardedHotPath:
             r = x.shape[1]
             m = self.b.ncols
             live = [i for i, csr in enumerate(self.ops) if csr is not None]
-            flat = torch.empty(len(live) * r * r + r * m, dtype=x.dtype, device=x.device)
+            nlive = len(live)
+            flat = torch.empty(nlive * r * r + r * m, dtype=x.dtype, device=x.device)
             g_list = [None] * len(self.ops)
             windows = {}
+            if self.pair is not None and r <= dv.SPMM2_MAX_R:    # one pass over the shared pattern for both operators
+                i0, i1 = self.pair
+                plan = self.plans[i0]
+                xin = x
+                if self.world > 1:
+                    self._win = exchange_halo(x, plan, self._win, group)
+                    xin = self._win[:plan.win1 - plan.win0]
+                y0, y1 = dv.spmm2(self.ops[i0], self.ops[i1], xin)
+                for k, (i, y) in enumerate(((i0, y0), (i1, y1))):
+                    g_list[i] = dv.gemm_tn(y, x, conj=False, out=flat[k * r * r:(k + 1) * r * r].view(r, r))
+                live = []
             for k, i in enumerate(live):
                 csr, plan = self.ops[i], self.plans[i]
                 dv.group_rows(csr, r)                # row-grouped operand, built once per operator on first use
@@ -275,7 +294,7 @@ class ShardedHotPath:
                 else:
                     y = dv.spmm(csr, x)
                 g_list[i] = dv.gemm_tn(y, x, conj=False, out=flat[k * r * r:(k + 1) * r * r].view(r, r))
-            bt = flat[len(live) * r * r:].view(r, m)
+            bt = flat[nlive * r * r:].view(r, m)
             bt.copy_(dv.project_rhs(self.b, x, self.row0, conj=False))
             allreduce_sum_(flat, group)
             return g_list, bt

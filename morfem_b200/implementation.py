@@ -157,6 +157,14 @@ class _DeviceOperators:
                     mark(i)
         self._a = [None, None, None]   # CSR of a itself, built lazily for the estimator (a_i @ q)
         self.b_host = csc_array(md.b)
+        # operators kept for many calls: compare the sparsity patterns once; two operators with one pattern (Ct and Tt of a
+        # FEM model) are then multiplied in one pass (device.spmm2).  One-shot uploads skip the host comparison.
+        self.pair = None
+        live = [i for i, z in enumerate(self.zero) if not z]
+        if self.grouped and len(live) == 2 and all(issparse(self.ops[i]) for i in live):
+            i0, i1 = live
+            if dv.mark_same_pattern(self.at[i0], self.at[i1], csc_array(self.ops[i0]), csc_array(self.ops[i1])):
+                self.pair = (i0, i1)
 
     def wait_ready(self, key=None):
         """Make the current stream wait for the side-stream upload of one operand (``key`` = operator index or "b") or of
@@ -175,6 +183,16 @@ class _DeviceOperators:
     def project_block(self, x):
         """``x^T (a_i x)`` for every operator and ``x^T b`` -- the callback of ``device.basis_and_projection``."""
         dv = self.dv
+        if self.pair is not None and x.shape[1] <= dv.SPMM2_MAX_R:
+            i0, i1 = self.pair
+            self.wait_ready(i0)
+            self.wait_ready(i1)
+            y0, y1 = dv.spmm2(self.at[i0], self.at[i1], x)
+            g_list = [None, None, None]
+            g_list[i0] = dv.gemm_tn(y0, x, conj=False)
+            g_list[i1] = dv.gemm_tn(y1, x, conj=False)
+            self.wait_ready("b")
+            return g_list, dv.project_rhs(self.b, x, 0, conj=False)
         g_list = []
         for i, (at, z) in enumerate(zip(self.at, self.zero)):
             if z:

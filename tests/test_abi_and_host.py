@@ -52,6 +52,8 @@ def test_argument_validation_without_gpu():
     assert lib.mf_trmm_nn_c128(None, 4, 10, 4, None, 4, None, 4, None) == -1
     assert lib.mf_chol_inv_upper_c128(None, 4, 4, None, 4, None, None, 0, None) == -1
     assert lib.mf_chol_inv_ws_bytes(256) >= 128
+    assert lib.mf_spmm_csr2_c128(None, None, None, None, 1, 10, None, 4, 4, None, 4, None, 4, None) == -1
+    assert lib.mf_spmm_csr2_f64(None, None, None, None, 10, None, 4, 4, None, 4, None, 4, None) == -1
     assert lib.mf_spmm_csr_f64(None, None, None, 10, None, 4, 4, None, 4, None) == -1
     assert lib.mf_spmm_group_count(None, None, 10, 4, None, None) == -1
     assert lib.mf_spmm_grouped_c128(None, None, None, 10, 4, None, 4, 4, None, 4, None) == -1

@@ -128,6 +128,30 @@ def test_jacobi_svd(dv, r, cmplx):
     assert 1 <= int(sweeps.item()) <= 40
 
 
+@pytest.mark.parametrize("r", [5, 64, 100, 256, 300])
+@pytest.mark.parametrize("real_q", [False, True])
+def test_two_operator_spmm_equals_two_single_passes(dv, r, real_q):
+    """mf_spmm_csr2_*: two operators with one sparsity pattern in one pass == the single-operator kernel twice (bit for bit:
+    same accumulation order) == scipy; operands with different patterns are refused."""
+    from morfem_b200 import synthetic
+    ct, tt = synthetic.waveguide_operators(6, 5, 30)
+    n = ct.shape[0]
+    rng = np.random.default_rng(r)
+    q = rng.standard_normal((n, r)) if real_q else crandn(rng, n, r)
+    qd = torch.from_numpy(np.ascontiguousarray(q)).cuda()
+    a0, a1 = dv.csr_of_transpose(ct), dv.csr_of_transpose(tt)
+    assert dv.mark_same_pattern(a0, a1, ct, tt) and dv.same_pattern(a0, a1)
+    y0, y1 = dv.spmm2(a0, a1, qd)
+    assert np.array_equal(y0.cpu().numpy(), dv.spmm(a0, qd).cpu().numpy())
+    assert np.array_equal(y1.cpu().numpy(), dv.spmm(a1, qd).cpu().numpy())
+    assert rel(y0.cpu().numpy(), ct.T @ q) < 1e-13 and rel(y1.cpu().numpy(), tt.T @ q) < 1e-13
+    other = sp.csc_array(sp.random(n, n, density=0.01, random_state=1, format="csc"))
+    b = dv.csr_of_transpose(other)
+    assert not dv.mark_same_pattern(a0, b, ct, other)
+    with pytest.raises(ValueError):
+        dv.spmm2(a0, b, qd)
+
+
 def test_symmetrize(dv):
     rng = np.random.default_rng(0)
     a = crandn(rng, 37, 37)
