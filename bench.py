@@ -347,10 +347,13 @@ def run_b200(args, wl, rank, world, local_rank):
         s_host = pin(s_loc)
         c_host, g_host, b_host = pinned_csc(in_c), pinned_csc(in_gamma), pinned_csc(in_b)
         out_pinned = torch.empty((f_total, wl["m"], wl["m"]), dtype=torch.complex128).pin_memory()
-        k_e2e = max(3, min(args.steps, 10))
-        for _ in range(2):
+        k_e2e = max(3, min(args.steps, 20))
+        for _ in range(3):
             th.model_order_reduction_gsm_from_snapshots(f, s_host, c_host, g_host, b_host, pinned_out=out_pinned, real_path=real)
         torch.cuda.synchronize()
+        import gc
+        gc.collect()
+        gc.disable()                                           # no collector pause inside the few-millisecond calls
         dv.transfer_bytes["h2d"] = dv.transfer_bytes["d2h"] = 0
         per_call = []
         t0 = time.perf_counter()
@@ -394,6 +397,7 @@ def run_b200(args, wl, rank, world, local_rank):
         e2e["operators_resident"] = {"value": f_total / dt_res, "unit": UNIT, "ms_per_step": dt_res * 1e3,
                                      "h2d_bytes_per_step": dv.transfer_bytes["h2d"] // k_e2e, "d2h_bytes_per_step": dv.transfer_bytes["d2h"] // k_e2e,
                                      "note": "same call with operators_resident=True: operators uploaded once, snapshot block uploaded every call"}
+        gc.enable()
         # sanity: the e2e result equals the device-resident result
         dev_gsm = out[0].cpu().numpy()
         if not np.allclose(gsm_host, dev_gsm, rtol=1e-9, atol=1e-12):
