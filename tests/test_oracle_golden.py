@@ -98,6 +98,23 @@ def test_cfg1_fixture_shipped_port_matrix_and_svd_pair():
     assert np.abs(np.abs(g["gsm_rom"][:, 0, 0]) ** 2 + np.abs(g["gsm_rom"][:, 1, 0]) ** 2 - 1.0).max() < 1e-6
 
 
+def test_full_order_sweep_matches_live_reference():
+    """``oracle.full_order_sweep`` (the sparse SuperLU branch, implementation.py:472-475) against the live reference's
+    ``finite_element_method_gsm`` (test_helpers.py:25-50) on the config-1 model with the shipped port matrix."""
+    from scipy.sparse import csc_array
+    g = load("cfg1_rom3411")
+    nx, ny, nz = (int(v) for v in g["grid"])
+    ct, tt = synthetic.waveguide_operators(nx, ny, nz)
+    wp = np.zeros((ct.shape[0], 2))
+    wp[g["wp_shipped_nz_rows"], g["wp_shipped_nz_cols"]] = g["wp_shipped_nz_vals"]
+    in_c, in_gamma, in_b = synthetic.driver_scaled(ct, tt, csc_array(wp))
+    f = g["f"]
+    x = orc.full_order_sweep(f, in_c, csc_array(in_c.shape), in_gamma, in_b, lambda t: 1.0, lambda t: t, lambda t: t ** 2, orc.b_coefficient)
+    gsm = orc.scattering_sweep(f, x, in_b.toarray())
+    assert x.shape == (f.size, ct.shape[0], 2)
+    assert orc.rel_err(gsm, g["gsm_full"]) < 1e-9
+
+
 def test_b_coefficient_raises_below_cutoff():
     with pytest.raises(ValueError):
         orc.b_coefficient(2.0e9)         # test_helpers.py:72: math.sqrt of a negative number
