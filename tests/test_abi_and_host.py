@@ -143,3 +143,22 @@ def test_full_order_branch_stays_on_scipy():
         x = impl.solve_fem_point(4e9, md)
     a = in_c + (4e9) ** 2 * in_gamma
     assert np.allclose(a @ x, th.b_coefficient(4e9) * in_b.toarray(), atol=1e-9 * np.abs(in_b.toarray()).max())
+
+
+def test_streamed_sweep_geometry_from_workspace_sizes(monkeypatch):
+    """The streamed sweep (113 <= r <= 512) sizes its workspace as one R x LD complex slot per resident CTA: three CTAs per SM
+    up to r = 128, two up to r = 256, one above (148 SMs assumed when no device is visible); MF_STREAM_CFG=0 forces one."""
+    from morfem_b200 import _ffi
+    lib = _ffi.load()
+    monkeypatch.delenv("MF_STREAM_CFG", raising=False)
+    slot = lambda r, m: 16 * ((r + 31) // 32 * 32) * ((r + 31) // 32 * 32 + (m + 7) // 8 * 8)
+    big = 10 ** 6
+    per_sm = {(113, 1): 3, (128, 4): 3, (129, 4): 2, (256, 4): 2, (257, 4): 1, (512, 8): 1}
+    sms = lib.mf_sweep_ws_bytes(512, 8, big, 3) // slot(512, 8)
+    assert sms >= 1
+    for (r, m), ctas in per_sm.items():
+        assert lib.mf_sweep_ws_bytes(r, m, big, 3) == ctas * sms * slot(r, m), (r, m)
+        assert lib.mf_sweep_ws_bytes(r, m, 10, 3) == 10 * slot(r, m)          # never more slots than points
+    monkeypatch.setenv("MF_STREAM_CFG", "0")
+    assert lib.mf_sweep_ws_bytes(256, 4, big, 3) == sms * slot(256, 4)
+    assert lib.mf_sweep_ws_bytes(64, 2, big, 3) <= 256                         # r <= 112: matrix lives in shared memory
