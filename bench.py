@@ -370,6 +370,7 @@ def run_b200(args, wl, rank, world, local_rank):
         e2e = {"value": f_total / dt, "unit": UNIT, "h2d_bytes_per_step": dv.transfer_bytes["h2d"] // k_e2e,
                "d2h_bytes_per_step": dv.transfer_bytes["d2h"] // k_e2e, "ms_per_step": dt * 1e3, "steps": k_e2e,
                "ms_per_call_median": float(np.median(per_call)) * 1e3, "ms_per_call_max": float(np.max(per_call)) * 1e3,
+               "ms_per_call": [round(t * 1e3, 3) for t in per_call],
                "call": "morfem_b200.test_helpers.model_order_reduction_gsm_from_snapshots (host ndarrays / scipy csc in pinned memory)"}
         # PCIe floor of that call: nothing but the same pinned host buffers copied to the device (what bounds e2e)
         bufs = [torch.from_numpy(s_host)] + [torch.from_numpy(np.asarray(x)) for a_ in (c_host, g_host, b_host) for x in (a_.data, a_.indices, a_.indptr)]
