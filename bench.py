@@ -1,24 +1,42 @@
 #!/usr/bin/env python
 """Benchmark of the reduced-order frequency-sweep hot path (BASELINE.json metric: reduced-sweep freq points/sec).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload cfg2|cfg3|small]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload cfg3|cfg2|cfg5|mid|small]
 
 One "step" = one pass of the four hot stages over one synthetic batch: orthonormalise the snapshot block
 (CholeskyQR2 + SVD of R), Galerkin-project Ct/Tt/WP, solve every reduced system, evaluate the S-parameters.
-``value`` = sweep points processed by all ranks / device time of K steps (inputs resident in HBM);
-``e2e``   = the same through the reference-facing Python call with HOST (pinned) inputs, H2D/D2H inside the timing.
-N > 1 (torchrun): weak scaling -- every rank holds one cfg-sized row block of the operators/snapshots and one
-block of sweep points; r x r partials are all-reduced, Q halo rows exchanged, S-parameters all-gathered.
+The default workload is the configuration the metric and the north-star target are quoted on (BASELINE configs[2]:
+N = 1M DOF, r = 256, 4 ports, 100k sweep points); it fits one B200.  ``--gpus N`` STRONG-scales it: the same global
+problem at every N, rows of the snapshot block / operators and the sweep points block-sharded over the ranks, r x r
+partials all-reduced, Q halo rows exchanged, S-parameters all-gathered.
 
-``--impl reference`` times the CPU restatement of the reference path (oracle/, numpy/scipy = the very library
-calls the pure-Python reference makes) on the host cores.
+``value`` = sweep points of the whole job / device time of K steps (inputs resident in HBM, max over ranks);
+``e2e``   = the same through the reference-facing Python call with HOST (pinned) inputs, H2D/D2H inside the timing;
+``parity``= the S-parameters of the timed configuration against the CPU restatement of the reference (oracle/);
+``--impl reference`` times that CPU restatement (numpy/scipy = the library calls the pure-Python reference makes)
+on all host cores of rank 0, each step a bounded sample of the same global workload.
 """
 from __future__ import annotations
 
-import argparse
-import json
 import os
 import sys
+
+
+def _host_cores() -> int:
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+# torchrun exports OMP_NUM_THREADS=1 to every rank.  The CPU legs (reference arm, cpu_baseline, parity) run on rank 0 only
+# and use all the host cores the process may run on -- set before numpy / OpenBLAS are loaded, and recorded in the line.
+if int(os.environ.get("RANK", "0")) == 0:
+    for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[_v] = str(_host_cores())
+
+import argparse
+import json
 import threading
 import time
 
@@ -28,36 +46,53 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOADS = {
-    # name: (grid nx, ny, nz per GPU), r, ports, sweep points per GPU
-    "cfg2": dict(grid=(20, 10, 1000), r=64, m=2, f=10000,
-                 desc="BASELINE configs[1]: synthetic curl-curl FEM N=200k DOF, r=64 basis, 2 ports, 10k freq points on 1 B200"),
-    "cfg3": dict(grid=(25, 20, 250), r=256, m=4, f=12500,
-                 desc="BASELINE configs[2]: synthetic N=1M DOF, r=256, 4 ports, 100k freq points sharded across 8 B200 "
-                      "(per GPU: 125k rows, 12.5k points; weak scaling below 8 GPUs)"),
-    "cfg5": dict(grid=(25, 20, 1000), r=512, m=8, f=125000,
-                 desc="BASELINE configs[4]: dense wideband sweep N=4M DOF, r=512, 8 ports, 1M freq points, row-sharded projection "
-                      "(per GPU at 8 GPUs: 500k rows, 125k points; weak scaling below 8 GPUs)"),
-    "small": dict(grid=(5, 4, 100), r=16, m=2, f=500, desc="smoke-sized workload"),
+    # name: GLOBAL grid (nx, ny, nz), r, ports, GLOBAL sweep points; cpu_points = points the CPU legs solve (scaled linearly)
+    "cfg3": dict(grid=(25, 20, 2000), r=256, m=4, f=100000, cpu_points=200,
+                 desc="BASELINE configs[2]: synthetic N=1M DOF, r=256, 4 ports, 100k freq points (the configuration the metric "
+                      "and the north-star target are quoted on); strong scaling over the GPUs"),
+    "cfg2": dict(grid=(20, 10, 1000), r=64, m=2, f=10000, cpu_points=2000,
+                 desc="BASELINE configs[1]: synthetic curl-curl FEM N=200k DOF, r=64 basis, 2 ports, 10k freq points"),
+    "cfg5": dict(grid=(25, 20, 8000), r=512, m=8, f=1000000, cpu_points=40,
+                 desc="BASELINE configs[4]: dense wideband sweep N=4M DOF, r=512, 8 ports, 1M freq points, row-sharded projection"),
+    "mid": dict(grid=(10, 8, 250), r=64, m=2, f=1024, cpu_points=1024, desc="parity-sized workload (N=20k, r=64, 2 ports, 1024 points)"),
+    "small": dict(grid=(5, 4, 100), r=16, m=2, f=512, cpu_points=512, desc="smoke-sized workload"),
 }
 METRIC = "reduced-sweep freq points/sec"
 UNIT = "points/s"
-FP64_PEAK_TFLOPS = 37.05   # measured on this pool's B200 by tools/fp64_peaks.cu (DMMA m8n8k4 issue loop; gpurun_out/fp64_peaks.jsonl)
+FP64_PEAK_FALLBACK = 37.05   # TFLOP/s, DMMA m8n8k4 issue loop measured on this pool's B200 in round 1 (profiles/r01_fp64_peaks.jsonl)
+SNAP_BLOCKS = 8              # the global snapshot block is 8 seeded row blocks, whatever the number of ranks
+EPS = float(np.finfo(np.float64).eps)
 
 
-def build_inputs(wl, world, rank):
-    """Seeded synthetic inputs.  The global problem is `world` copies of the per-GPU grid stacked
-    along z; returns the GLOBAL operators (scipy, host), this rank's snapshot rows and the global frequency axis."""
+def workload_config(name, wl, n):
+    """The ``config`` object of the JSON line -- identical for the b200 and the reference arm."""
+    return {"workload": name + ": " + wl["desc"], "N_dof_total": int(n), "r": wl["r"], "ports": wl["m"], "freq_points_total": wl["f"],
+            "scaling": "strong: one global problem, rows and sweep points block-sharded over the GPUs",
+            "l2": "inputs larger than L2 (snapshot block %.0f MB complex128 + operators); no flush" % (n * wl["r"] * 16 / 1e6)}
+
+
+def snapshot_rows(n, r, lo, hi):
+    """Rows [lo, hi) of the global synthetic snapshot block: SNAP_BLOCKS independently seeded row blocks."""
     from morfem_b200 import synthetic, dist as mfd
+    parts = []
+    for b in range(SNAP_BLOCKS):
+        b0, b1 = mfd.even_split(n, SNAP_BLOCKS, b)
+        s0, s1 = max(lo, b0), min(hi, b1)
+        if s1 > s0:
+            blk = synthetic.snapshot_matrix(b1 - b0, r, seed=1000 + b, decay_decades=6.0)
+            parts.append(blk[s0 - b0:s1 - b0])
+    return np.ascontiguousarray(np.concatenate(parts, axis=0)) if len(parts) != 1 else np.ascontiguousarray(parts[0])
+
+
+def build_operators(wl):
+    from morfem_b200 import synthetic
     nx, ny, nz = wl["grid"]
-    ct, tt = synthetic.waveguide_operators(nx, ny, nz * world)
+    ct, tt = synthetic.waveguide_operators(nx, ny, nz)
     n = ct.shape[0]
     wp = synthetic.port_matrix(n, wl["m"], 19)
     in_c, in_gamma, in_b = synthetic.driver_scaled(ct, tt, wp)
-    f = synthetic.frequency_points(wl["f"] * world)
-    row0, row1 = mfd.even_split(n, world, rank)
-    # per-rank seed: rows are independent Gaussian columns, so a per-block seed gives a valid global block
-    s_loc = synthetic.snapshot_matrix(row1 - row0, wl["r"], seed=1000 + rank, decay_decades=6.0)
-    return in_c, in_gamma, in_b, f, s_loc, n
+    f = synthetic.frequency_points(wl["f"])
+    return in_c, in_gamma, in_b, f, n
 
 
 class ClockSampler(threading.Thread):
@@ -119,27 +154,51 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
-# ------------------------------------------------------------------------------------------ reference arm
-def cpu_hot_path_timed(in_c, in_gamma, in_b, f, s, f_sample):
-    """Time the CPU restatement of the reference path (oracle) stage by stage; stages 3+4 on ``f_sample`` points
-    spread over the axis and scaled linearly to the full axis (the loop is per-point independent)."""
+# ------------------------------------------------------------------------------------------ CPU legs (oracle)
+def sample_indices(f_total, count):
+    return np.unique(np.linspace(0, f_total - 1, min(int(count), int(f_total))).astype(np.int64))
+
+
+def cpu_stage12(in_c, in_gamma, in_b, s):
+    """Stages 1 + 2 of the CPU restatement of the reference on the given rows (implementation.py:226, :181-184)."""
     from scipy.sparse import csc_array
     from oracle import reference_path as orc
-    idx = np.linspace(0, f.size - 1, min(f_sample, f.size)).astype(int)
-    fs = f[idx]
     t0 = time.perf_counter()
-    q = orc.orthonormal_basis(s)                                                    # implementation.py:226
+    q = orc.orthonormal_basis(s)
     t1 = time.perf_counter()
-    a0_r, a1_r, a2_r, b_r = orc.galerkin_projection(q, in_c, csc_array(in_c.shape), in_gamma, in_b)   # :181-184
+    red = orc.galerkin_projection(q, in_c, csc_array(in_c.shape), in_gamma, in_b)
     t2 = time.perf_counter()
-    x = orc.reduced_sweep(fs, a0_r, a1_r, a2_r, b_r, lambda t: 1.0, lambda t: t, lambda t: t ** 2, orc.b_coefficient)  # :189-194
-    t3 = time.perf_counter()
-    gsm = orc.scattering_sweep(fs, x, b_r)                                          # test_helpers.py:60-65
-    t4 = time.perf_counter()
-    scale = f.size / fs.size
-    total = (t2 - t0) + (t4 - t2) * scale
-    return {"basis_s": t1 - t0, "projection_s": t2 - t1, "sweep_s_per_point": (t3 - t2) / fs.size,
-            "gsm_s_per_point": (t4 - t3) / fs.size, "step_s_full_axis": total, "points_sampled": int(fs.size)}, gsm
+    return red, {"basis_s": t1 - t0, "projection_s": t2 - t1}
+
+
+def cpu_sweep(fs, red):
+    """Stages 3 + 4 of the CPU restatement on the points ``fs`` (implementation.py:189-194, test_helpers.py:60-65)."""
+    from oracle import reference_path as orc
+    a0_r, a1_r, a2_r, b_r = red
+    t0 = time.perf_counter()
+    x = orc.reduced_sweep(fs, a0_r, a1_r, a2_r, b_r, lambda t: 1.0, lambda t: t, lambda t: t ** 2, orc.b_coefficient)
+    t1 = time.perf_counter()
+    gsm = orc.scattering_sweep(fs, x, b_r)
+    t2 = time.perf_counter()
+    return gsm, {"sweep_s_per_point": (t1 - t0) / fs.size, "gsm_s_per_point": (t2 - t1) / fs.size, "points_sampled": int(fs.size)}
+
+
+def system_conds(fs, red):
+    from oracle import reference_path as orc
+    a0_r, a1_r, a2_r, _ = red
+    return np.array([np.linalg.cond(orc.system_matrix(1.0, t, t ** 2, a0_r, a1_r, a2_r)) for t in fs])
+
+
+def snapshot_cond(s):
+    """cond(S) from the eigenvalues of the Gram matrix (an estimate good to a few digits for cond up to ~1e7)."""
+    w = np.linalg.eigvalsh(s.T @ s)
+    return float(np.sqrt(w[-1] / max(w[0], w[-1] * 1e-15)))
+
+
+def per_point_rel(new, ref):
+    new = np.asarray(new).reshape(new.shape[0], -1)
+    ref = np.asarray(ref).reshape(ref.shape[0], -1)
+    return np.linalg.norm(new - ref, axis=1) / np.linalg.norm(ref, axis=1)
 
 
 def blas_threads():
@@ -147,34 +206,53 @@ def blas_threads():
         import threadpoolctl
         return max([p.get("num_threads", 1) for p in threadpoolctl.threadpool_info()] + [1])
     except Exception:
-        return os.cpu_count() or 1
+        return _host_cores()
 
 
-def run_reference(args, wl, rank, world):
+def run_reference(args, name, wl, rank, world):
+    """The reference's CPU implementation of the path (oracle port: the reference is pure Python, its arithmetic is the very
+    numpy/scipy calls made here), all host cores, the same GLOBAL workload at every N.  One step = a bounded sample:
+    stages 1+2 on the leading ``cpu_rows`` rows (cost linear in N, scaled), stages 3+4 on ``cpu_points`` points (scaled)."""
     if rank != 0:
         return
-    in_c, in_gamma, in_b, f, s_loc, n = build_inputs(wl, 1, 0)
-    f_sample = min(f.size, args.cpu_points)
+    nx, ny, nz = wl["grid"]
+    n = nx * ny * nz
+    r = wl["r"]
+    # the row sample is a shorter waveguide of the same cross-section (same band structure and non-zeros per row, so the same
+    # cost per row), with its own port matrix so that the sampled reduced model is a regular one
+    nz_s = min(nz, max(2 * 19 // (nx * ny) + 2, args.cpu_rows // (nx * ny)))
+    sub_c, sub_g, sub_b, f, rows = build_operators(dict(wl, grid=(nx, ny, nz_s)))
+    s = snapshot_rows(n, r, 0, rows)
+    idx = sample_indices(f.size, args.cpu_points or wl["cpu_points"])
+    fs = f[idx]
+
+    def one_step():
+        red, t12 = cpu_stage12(sub_c, sub_g, sub_b, s)
+        _, t34 = cpu_sweep(fs, red)
+        t12["step_s_full"] = (t12["basis_s"] + t12["projection_s"]) * (n / rows) + (t34["sweep_s_per_point"] + t34["gsm_s_per_point"]) * f.size
+        t12.update(t34)
+        return t12
+
     for _ in range(args.warmup):
-        cpu_hot_path_timed(in_c, in_gamma, in_b, f, s_loc, max(8, f_sample // 16))
+        one_step()
     times = []
     t_start = time.perf_counter()
     for _ in range(args.steps):
-        t, _ = cpu_hot_path_timed(in_c, in_gamma, in_b, f, s_loc, f_sample)
-        times.append(t)
+        times.append(one_step())
     wall = time.perf_counter() - t_start
-    step_s = float(np.mean([t["step_s_full_axis"] for t in times]))
+    step_s = float(np.mean([t["step_s_full"] for t in times]))
     value = f.size / step_s
     cores = blas_threads()
-    sample = (f"stages 1+2 in full (N={n}, r={wl['r']}), stages 3+4 on {times[0]['points_sampled']} of {f.size} points scaled linearly; "
-              f"numpy/scipy = the reference's own library calls (oracle port), real float64 (the reference's dtype)")
+    sample = (f"per step: stages 1+2 on the leading {rows} of {n} rows (r={r}; cost linear in N, scaled by {n / rows:.1f}), stages 3+4 on "
+              f"{fs.size} of {f.size} points scaled linearly; numpy/scipy = the reference's own library calls (oracle port), real float64 "
+              f"(the reference's dtype), {cores} BLAS threads on {_host_cores()} host cores")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": args.workload + ": " + wl["desc"], "note": "CPU arm runs the single-GPU workload on rank 0's host cores"},
+            "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(name, wl, n),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "stages": {"basis_ms": float(np.mean([t["basis_s"] for t in times])) * 1e3,
-                       "projection_ms": float(np.mean([t["projection_s"] for t in times])) * 1e3,
+            "stages": {"basis_ms_full": float(np.mean([t["basis_s"] for t in times])) * 1e3 * n / rows,
+                       "projection_ms_full": float(np.mean([t["projection_s"] for t in times])) * 1e3 * n / rows,
                        "sweep_us_per_point": float(np.mean([t["sweep_s_per_point"] for t in times])) * 1e6,
                        "gsm_us_per_point": float(np.mean([t["gsm_s_per_point"] for t in times])) * 1e6},
             "wall_s": wall}
@@ -182,28 +260,92 @@ def run_reference(args, wl, rank, world):
 
 
 # ---------------------------------------------------------------------------------------------- B200 arm
-def run_b200(args, wl, rank, world, local_rank):
+def measure_fp64_peak():
+    """FP64 tensor-pipe (DMMA) peak measured live by the library's issue-loop kernel (mf_peak_dmma_tflops)."""
+    import ctypes
+    import torch
+    from morfem_b200 import _ffi
+    lib = _ffi.load()
+    out = ctypes.c_double(0.0)
+    try:
+        st = lib.mf_peak_dmma_tflops(4096, ctypes.byref(out), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    except AttributeError:
+        return FP64_PEAK_FALLBACK, "fallback: 37.05 TFLOP/s measured in round 1 (profiles/r01_fp64_peaks.jsonl)"
+    if st != 0 or not (out.value > 1.0):
+        return FP64_PEAK_FALLBACK, "fallback: 37.05 TFLOP/s measured in round 1 (profiles/r01_fp64_peaks.jsonl)"
+    return float(out.value), ("FP64 tensor-pipe (DMMA m8n8k4) issue-loop peak measured in this run by mf_peak_dmma_tflops; "
+                             "MEASURED_PEAKS.json holds no FP64 figure and its bf16 figure does not bound an FP64 kernel")
+
+
+def make_path(wl_ops, rank, world):
+    from scipy.constants import pi, epsilon_0
+    from scipy.sparse import csc_array
+    from morfem_b200 import dist as mfd, implementation as impl, test_helpers as th
+    in_c, in_gamma, in_b, f, n = wl_ops
+    cb = impl.coefficient_array(th.b_coefficient, f)
+    coeffs = [np.ones_like(f), f, f ** 2, cb, 2 * pi * f * epsilon_0]
+    return mfd.ShardedHotPath([in_c, csc_array(in_c.shape), in_gamma], in_b, n, f.size, coeffs)
+
+
+def parity_small(world, rank, dev, real):
+    """N > 1: before timing, the sharded path on a reduced-size GLOBAL problem against the CPU oracle on rank 0 -- halo-window
+    SpMM, all-reduced Gram / projection partials and the gathered S-parameters, on the hardware the timing runs on."""
     import torch
     import torch.distributed as dist
-    from scipy.constants import pi, epsilon_0
-    from morfem_b200 import device as dv, dist as mfd, _ffi, implementation as impl, test_helpers as th
+    from morfem_b200 import device as dv, dist as mfd
+    wl = WORKLOADS["mid"]
+    ops = build_operators(wl)
+    in_c, in_gamma, in_b, f, n = ops
+    path = make_path(ops, rank, world)
+    lo, hi = mfd.even_split(n, world, rank)
+    s_dev = dv.real_or_complex_to_device(snapshot_rows(n, wl["r"], lo, hi), dev, widen=not real)
+    gsm, q, red, res = path.step(s_dev, want_x=False, gather=True)
+    torch.cuda.synchronize()
+    out = None
+    if rank == 0:
+        s_glob = snapshot_rows(n, wl["r"], 0, n)
+        ref_red, _ = cpu_stage12(in_c, in_gamma, in_b, s_glob)
+        ref_gsm, _ = cpu_sweep(f, ref_red)
+        cond = system_conds(f, ref_red)
+        tol = np.maximum(1e-10, 50 * EPS * np.maximum(cond, snapshot_cond(s_glob)))
+        err = per_point_rel(gsm.cpu().numpy(), ref_gsm)
+        out = {"workload": "mid: " + wl["desc"] + f", sharded over {world} ranks", "max_rel_err": float(err.max()), "points": int(f.size),
+               "tol_max": float(tol.max()), "worst_err_over_tol": float((err / tol).max()), "ok": bool(np.all(err < tol))}
+    ok = torch.tensor([1 if (out is None or out["ok"]) else 0], device=dev)
+    dist.broadcast(ok, 0)
+    if int(ok.item()) != 1:
+        raise SystemExit(f"bench: multi-rank parity against the CPU oracle FAILED: {out}")
+    del path
+    return out
+
+
+def run_b200(args, name, wl, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from scipy.sparse import csc_array
+    from morfem_b200 import device as dv, dist as mfd, _ffi, test_helpers as th
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    lib = _ffi.load()
+    _ffi.load()
+    fp64_peak, fp64_src = measure_fp64_peak()
 
-    in_c, in_gamma, in_b, f, s_loc, n = build_inputs(wl, world, rank)
-    from scipy.sparse import csc_array
-    cb = impl.coefficient_array(th.b_coefficient, f)
-    coeffs = [np.ones_like(f), f, f ** 2, cb, 2 * pi * f * epsilon_0]
-    path = mfd.ShardedHotPath([in_c, csc_array(in_c.shape), in_gamma], in_b, n, f.size, coeffs)
     # "c128" (default, the north star's arithmetic): the real synthetic data embedded in complex128, complex128 kernels
     # throughout.  The synthetic operators and snapshots are real, like the reference's data (main.py:21-23), so "auto" /
     # "f64" run the real float64 twins -- what the public API selects by itself for such inputs; the default run times
     # that path too and reports it under "other_dtype".
     real = args.dtype in ("auto", "f64")
+
+    parity_pre = parity_small(world, rank, dev, real) if (world > 1 and not args.no_parity) else None
+
+    ops = build_operators(wl)
+    in_c, in_gamma, in_b, f, n = ops
+    r, m = wl["r"], wl["m"]
+    path = make_path(ops, rank, world)
+    row0, row1 = mfd.even_split(n, world, rank)
+    s_loc = snapshot_rows(n, r, row0, row1)
     s_dev = dv.real_or_complex_to_device(s_loc, dev, widen=not real)
     f_total = f.size
 
@@ -213,76 +355,120 @@ def run_b200(args, wl, rank, world, local_rank):
             dist.barrier()
             torch.cuda.synchronize()
 
-    use_graph = world == 1 and not args.no_graph
+    use_graph = not args.no_graph and (world == 1 or path.graph_capable)
 
-    def step():
-        if use_graph:
-            return path.step_graph(s_dev, want_x=False)       # whole step replayed from one CUDA graph
-        return path.step_deferred(s_dev, want_x=False, gather=True)   # eager launches, CholeskyQR2 flags verified after the loop
+    def make_step(s_in):
+        def step():
+            if use_graph:
+                return path.step_graph(s_in, want_x=False)        # whole step replayed from one CUDA graph
+            return path.step_deferred(s_in, want_x=False, gather=True)   # eager launches, CholeskyQR2 flags verified after the loop
+        return step
 
-    for _ in range(max(args.warmup, 3)):
+    def check_flags(what):
+        ok = (path.verify() is None) if use_graph else path.verify_deferred()
+        if not ok:
+            raise SystemExit(f"bench: optimistic CholeskyQR2 failed verification on the synthetic snapshot block ({what})")
+
+    def timed(step, k, w):
+        for _ in range(w):
+            out_ = step()
+        barrier()
+        l0 = _ffi.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k):
+            out_ = step()
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()) / k, out_, _ffi.launch_count() - l0
+
+    step = make_step(s_dev)
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
         out = step()
     barrier()
-    launches0 = _ffi.launch_count()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    for _ in range(args.steps):
-        out = step()
-    e1.record()
-    barrier()
+    ms_step, out, launches = timed(step, args.steps, 0)
     clocks = sampler.stop()
-    launches = _ffi.launch_count() - launches0
-    if not use_graph and not path.verify_deferred():
-        raise SystemExit("bench: optimistic CholeskyQR2 failed verification on the synthetic snapshot block")
+    check_flags("timed loop")
     if use_graph:
-        # a graph replay launches the captured kernels without passing through the C ABI's counter
-        launches = args.steps * path.launches_per_graph
-        if path.verify() is not None:
-            raise SystemExit("bench: optimistic CholeskyQR2 failed verification on the synthetic snapshot block")
-    ms_total = e0.elapsed_time(e1)
-    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = float(t.item())
-    ms_step = ms_total / args.steps
+        launches = args.steps * path.launches_per_graph          # a replay launches the captured kernels without passing the ABI counter
     value = f_total / (ms_step * 1e-3)
+    gsm_dev = out[0]
+    reduced_dev = out[2]
+
+    # ---- parity of the timed configuration against the CPU restatement of the reference (rank 0, sampled points)
+    parity, cpu_baseline = None, None
+    if rank == 0 and not args.no_parity:
+        idx = sample_indices(f_total, args.cpu_points or wl["cpu_points"])
+        fs = f[idx]
+        g_gpu = gsm_dev[torch.from_numpy(idx).to(dev)].cpu().numpy()
+        red_gpu = [np.zeros((r, r)) if o is None else o.cpu().numpy() for o in reduced_dev[:3]] + [reduced_dev[3].cpu().numpy()]
+        red_gpu = [np.ascontiguousarray(a.real) for a in red_gpu]          # real data stays exactly real on the complex128 path
+        # (a) stage isolated: the CPU sweep (lu_factor/lu_solve + the S-parameter algebra) on the reduced model the GPU produced
+        g_iso, t34 = cpu_sweep(fs, red_gpu)
+        cond = system_conds(fs, red_gpu)
+        tol_iso = np.maximum(1e-10, 20 * EPS * cond)
+        e_iso = per_point_rel(g_gpu, g_iso)
+        parity = {"points": int(fs.size), "tol": "max(1e-10, 20 eps cond(A(t))) per point (stage isolated); chained: eps-level "
+                  "changes of S move span(S) by eps cond(S), so max(1e-10, 50 eps max(cond(A(t)), cond(S)))",
+                  "stage_isolated": {"max_rel_err": float(e_iso.max()), "median_rel_err": float(np.median(e_iso)), "tol_max": float(tol_iso.max()),
+                                     "worst_err_over_tol": float((e_iso / tol_iso).max()), "cond_max": float(cond.max())}}
+        ok = bool(np.all(e_iso < tol_iso))
+        full = args.parity == "full" or (args.parity == "auto" and world == 1 and n * r * r <= 1.1e6 * 256 * 256)
+        if full:
+            # (b) chained: the whole path on the CPU (svd, projection, LU sweep, S-parameters) -- also the cpu_baseline figure
+            s_glob = s_loc if world == 1 else snapshot_rows(n, r, 0, n)
+            ref_red, t12 = cpu_stage12(in_c, in_gamma, in_b, s_glob)
+            g_ref, t34 = cpu_sweep(fs, ref_red)
+            cond_ref = system_conds(fs, ref_red)
+            cond_s = snapshot_cond(s_glob)
+            tol_ch = np.maximum(1e-10, 50 * EPS * np.maximum(cond_ref, cond_s))
+            e_ch = per_point_rel(g_gpu, g_ref)
+            parity["chained"] = {"max_rel_err": float(e_ch.max()), "median_rel_err": float(np.median(e_ch)), "tol_max": float(tol_ch.max()),
+                                 "worst_err_over_tol": float((e_ch / tol_ch).max()), "cond_S": cond_s}
+            parity["max_rel_err"] = float(e_ch.max())
+            ok = ok and bool(np.all(e_ch < tol_ch))
+            step_s = t12["basis_s"] + t12["projection_s"] + (t34["sweep_s_per_point"] + t34["gsm_s_per_point"]) * f_total
+            cpu_baseline = {"value": f_total / step_s, "unit": UNIT, "cores": blas_threads(), "kind": "port",
+                            "sample": f"one pass: stages 1+2 in full (N={n}, r={r}: svd {t12['basis_s']:.2f} s, projection {t12['projection_s']:.2f} s), "
+                                      f"stages 3+4 on {t34['points_sampled']} of {f_total} points ({t34['sweep_s_per_point'] * 1e6:.0f} + "
+                                      f"{t34['gsm_s_per_point'] * 1e6:.0f} us/point) scaled linearly; real float64 like the reference"}
+            del s_glob
+        else:
+            parity["max_rel_err"] = float(e_iso.max())
+        parity["ok"] = ok
+        if parity_pre is not None:
+            parity["multi_rank_small_problem"] = parity_pre
+    if not args.no_parity:
+        flag = torch.tensor([1 if (parity is None or parity["ok"]) else 0], device=dev)
+        if world > 1:
+            dist.broadcast(flag, 0)
+        if int(flag.item()) != 1:
+            raise SystemExit(f"bench: parity against the CPU oracle FAILED: {json.dumps(parity)}")
 
     # ---- the same timed loop on the other arithmetic type (same data; complex128 kernels <-> real float64 twins)
     alt = None
     if not args.no_alt_dtype:
         s_alt = dv.real_or_complex_to_device(s_loc, dev, widen=real)
-
-        def step_alt():
-            if use_graph:
-                return path.step_graph(s_alt, want_x=False)
-            return path.step_deferred(s_alt, want_x=False, gather=True)
-
-        for _ in range(max(args.warmup, 3)):
-            step_alt()
-        barrier()
-        a0_, a1_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a0_.record()
-        for _ in range(args.steps):
-            step_alt()
-        a1_.record()
-        barrier()
-        ta = torch.tensor([a0_.elapsed_time(a1_)], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(ta, op=dist.ReduceOp.MAX)
-        ms_alt = float(ta.item()) / args.steps
-        if (use_graph and path.verify() is not None) or (not use_graph and not path.verify_deferred()):
-            raise SystemExit("bench: optimistic CholeskyQR2 failed verification (alternate dtype)")
+        ms_alt, out_alt, _ = timed(make_step(s_alt), args.steps, warm)
+        check_flags("alternate dtype")
+        if rank == 0:
+            da = per_point_rel(out_alt[0][::max(1, f_total // 512)].cpu().numpy(), gsm_dev[::max(1, f_total // 512)].cpu().numpy())
         alt = {"dtype": "c128" if real else "f64", "value": f_total / (ms_alt * 1e-3), "unit": UNIT, "ms_per_step": ms_alt,
+               "max_rel_diff_vs_primary": float(da.max()) if rank == 0 else None,
                "note": "same workload and timed loop on the other arithmetic type: " +
                        ("real data embedded in complex128, complex128 kernels throughout (the north star's kernels)" if real
-                        else "real float64 twins of every kernel")}
-        del s_alt
+                        else "real float64 twins of every kernel (the reference's own dtype)")}
+        del s_alt, out_alt
+        path.drop_graph()
 
     # ---- per-kernel and per-stage timing (CUDA events on the launching stream, separate pass over the same steps)
-    prof_steps = max(1, min(args.steps, 5))
+    prof_steps = max(1, min(args.steps, 3))
     for _ in range(2):                                        # eager warm-up (the timed loop above may have been graph replays)
         path.step(s_dev, want_x=False, gather=True)
     barrier()
@@ -303,17 +489,20 @@ def run_b200(args, wl, rank, world, local_rank):
     peak_src = "MEASURED_PEAKS.json hbm_gbs (measured)" if have_peaks else "fallback 6650 GB/s"
     kernels = {}
     dominant, dom_ms, all_ms = None, -1.0, 0.0
-    for name, a in agg.items():
+    for kname, a in agg.items():
         ms_call = a["ms"] / a["calls"]
-        kernels[name] = {"calls_per_step": a["calls"] / prof_steps, "ms_per_call": ms_call, "ms_per_step": a["ms"] / prof_steps,
-                         "GBps": a["bytes"] / a["calls"] / ms_call / 1e6 if ms_call > 0 else None,
-                         "TFLOPs": a["flops"] / a["calls"] / ms_call / 1e9 if ms_call > 0 else None}
+        kernels[kname] = {"calls_per_step": a["calls"] / prof_steps, "ms_per_call": ms_call, "ms_per_step": a["ms"] / prof_steps,
+                          "GBps": a["bytes"] / a["calls"] / ms_call / 1e6 if ms_call > 0 else None,
+                          "TFLOPs": a["flops"] / a["calls"] / ms_call / 1e9 if ms_call > 0 else None}
         all_ms += a["ms"]
         if a["ms"] > dom_ms:
-            dominant, dom_ms = name, a["ms"]
-    traffic = {}
+            dominant, dom_ms = kname, a["ms"]
+    traffic, traffic_src = None, None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        ent = tr.get(f"{name}:{'f64' if real else 'c128'}:{dominant}")
+        if ent:
+            traffic, traffic_src = ent["bytes_per_launch_at_bench_size"], ent["source"]
     except Exception:
         pass
     roof = None
@@ -321,18 +510,17 @@ def run_b200(args, wl, rank, world, local_rank):
         a = agg[dominant]
         ms_call = kernels[dominant]["ms_per_call"]
         t_mem = a["bytes"] / a["calls"] / (hbm_peak * 1e9)
-        t_flop = a["flops"] / a["calls"] / (FP64_PEAK_TFLOPS * 1e12)
-        share = {"share_of_timed_kernels": dom_ms / all_ms, "share_of_step": (dom_ms / prof_steps) / ms_step}
+        t_flop = a["flops"] / a["calls"] / (fp64_peak * 1e12)
+        share = {"share_of_timed_kernels": dom_ms / all_ms, "share_of_step": (dom_ms / prof_steps) / ms_step,
+                 "traffic_source": traffic_src or "no ncu capture of this kernel at this size is committed"}
         if t_flop >= t_mem:
             ach = a["flops"] / a["calls"] / (ms_call * 1e-3) / 1e12
-            roof = {"kernel": dominant, "bound": "tensor", "achieved": ach, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": ach / FP64_PEAK_TFLOPS,
-                    "traffic": (traffic.get(dominant) or {}).get("bytes") if (args.workload == "cfg2" and not real) else None, "peak_source": "FP64 tensor-pipe (DMMA) peak measured on this pool's B200 by tools/fp64_peaks.cu; "
-                                                    "MEASURED_PEAKS.json holds no FP64 figure and its bf16 figure does not bound an FP64 kernel", **share}
+            roof = {"kernel": dominant, "bound": "tensor", "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach / fp64_peak,
+                    "traffic": traffic, "peak_source": fp64_src, **share}
         else:
             ach = a["bytes"] / a["calls"] / (ms_call * 1e-3) / 1e9
             roof = {"kernel": dominant, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
-                    "traffic": (traffic.get(dominant) or {}).get("bytes") if (args.workload == "cfg2" and not real) else None,
-                    "peak_source": peak_src, **share}
+                    "traffic": traffic, "peak_source": peak_src, **share}
 
     # ---- end to end through the reference-facing call, host (pinned) buffers in, host array out (rank-local job)
     e2e = None
@@ -346,13 +534,14 @@ def run_b200(args, wl, rank, world, local_rank):
 
         s_host = pin(s_loc)
         c_host, g_host, b_host = pinned_csc(in_c), pinned_csc(in_gamma), pinned_csc(in_b)
-        out_pinned = torch.empty((f_total, wl["m"], wl["m"]), dtype=torch.complex128).pin_memory()
-        k_e2e = max(3, min(args.steps, 20))
+        out_pinned = torch.empty((f_total, m, m), dtype=torch.complex128).pin_memory()
+        k_e2e = max(3, min(args.steps, 20 if ms_step < 50 else 5))
         # the call allocates its device buffers on two streams (compute and upload): start from an empty cache and warm the
         # allocator's per-stream pools up, otherwise some timed calls pay a cudaMalloc (seen as 20-50 ms outliers)
+        path.drop_graph()
         torch.cuda.synchronize()
         torch.cuda.empty_cache()
-        for _ in range(6):
+        for _ in range(6 if ms_step < 50 else 3):
             th.model_order_reduction_gsm_from_snapshots(f, s_host, c_host, g_host, b_host, pinned_out=out_pinned, real_path=real)
         torch.cuda.synchronize()
         import gc
@@ -388,31 +577,21 @@ def run_b200(args, wl, rank, world, local_rank):
         e2e["h2d_copy_floor"] = {"ms": copy_ms, "bytes": copy_bytes, "GBps": copy_bytes / copy_ms / 1e6,
                                  "note": "the same pinned input buffers copied host->device with nothing else running"}
         del dsts
-        # the same call with the FEM operators kept on the device between calls (the model is fixed, the snapshot block is
-        # the per-step input): H2D = the snapshot block only
-        for _ in range(4):
-            th.model_order_reduction_gsm_from_snapshots(f, s_host, c_host, g_host, b_host, pinned_out=out_pinned, real_path=real, operators_resident=True)
-        torch.cuda.synchronize()
-        dv.transfer_bytes["h2d"] = dv.transfer_bytes["d2h"] = 0
-        t0 = time.perf_counter()
-        for _ in range(k_e2e):
-            th.model_order_reduction_gsm_from_snapshots(f, s_host, c_host, g_host, b_host, pinned_out=out_pinned, real_path=real, operators_resident=True)
-        torch.cuda.synchronize()
-        dt_res = (time.perf_counter() - t0) / k_e2e
-        e2e["operators_resident"] = {"value": f_total / dt_res, "unit": UNIT, "ms_per_step": dt_res * 1e3,
-                                     "h2d_bytes_per_step": dv.transfer_bytes["h2d"] // k_e2e, "d2h_bytes_per_step": dv.transfer_bytes["d2h"] // k_e2e,
-                                     "note": "same call with operators_resident=True: operators uploaded once, snapshot block uploaded every call"}
         gc.enable()
         # sanity: the e2e result equals the device-resident result
-        dev_gsm = out[0].cpu().numpy()
-        if not np.allclose(gsm_host, dev_gsm, rtol=1e-9, atol=1e-12):
+        sub = slice(None, None, max(1, f_total // 2048))
+        d_e2e = per_point_rel(gsm_host[sub], gsm_dev[sub].cpu().numpy())
+        e2e["max_rel_diff_vs_device_resident"] = float(d_e2e.max())
+        if not np.all(d_e2e < 1e-8):
             raise SystemExit("bench: e2e and device-resident S-parameters disagree")
     else:
         # N > 1: the public multi-GPU call is ShardedHotPath.step on device-resident shards; its e2e adds the per-rank
         # snapshot upload and the S-parameter download
         s_host = torch.from_numpy(np.ascontiguousarray(s_loc)).pin_memory()
-        out_pinned = torch.empty((f_total, wl["m"], wl["m"]), dtype=torch.complex128).pin_memory()
+        out_pinned = torch.empty((f_total, m, m), dtype=torch.complex128).pin_memory()
         k_e2e = max(3, min(args.steps, 10))
+        for _ in range(2):
+            path.step(s_dev, want_x=False, gather=True)
         barrier()
         t0 = time.perf_counter()
         for _ in range(k_e2e):
@@ -426,78 +605,83 @@ def run_b200(args, wl, rank, world, local_rank):
         tt_ = torch.tensor([dt], dtype=torch.float64, device=dev)
         dist.all_reduce(tt_, op=dist.ReduceOp.MAX)
         dt = float(tt_.item())
-        e2e = {"value": f_total / dt, "unit": UNIT, "h2d_bytes_per_step": int(s_host.numel() * 8), "d2h_bytes_per_step": int(out_pinned.numel() * 16),
+        e2e = {"value": f_total / dt, "unit": UNIT, "h2d_bytes_per_step": int(s_host.numel() * 8) * world, "d2h_bytes_per_step": int(out_pinned.numel() * 16),
                "ms_per_step": dt * 1e3, "steps": k_e2e, "call": "morfem_b200.dist.ShardedHotPath.step (per-rank snapshot rows from pinned host memory)"}
 
-    cpu_baseline = None
-    if world == 1 and rank == 0 and not args.no_cpu_baseline:
-        tcpu, _ = cpu_hot_path_timed(in_c, in_gamma, in_b, f, s_loc, min(f.size, args.cpu_points))
-        cpu_baseline = {"value": f.size / tcpu["step_s_full_axis"], "unit": UNIT, "cores": blas_threads(), "kind": "port",
-                        "sample": f"one pass: stages 1+2 in full (N={n}, r={wl['r']}, svd {tcpu['basis_s']:.2f} s, projection {tcpu['projection_s']:.2f} s), "
-                                  f"stages 3+4 on {tcpu['points_sampled']} of {f.size} points ({tcpu['sweep_s_per_point'] * 1e6:.0f} + "
-                                  f"{tcpu['gsm_s_per_point'] * 1e6:.0f} us/point) scaled linearly; real float64 like the reference"}
-
-    # ---- stages 1+2 alone, device timed (single rank: replayed from their own CUDA graph; N > 1: eager launches)
+    # ---- stages 1+2 alone, device timed (CUDA graph where the step is captured; else eager launches)
     bp_alone_ms = None
     try:
         def step12():
             if use_graph:
                 return path.step_graph(s_dev, want_x=False, skip_sweep=True)
             return path.step(s_dev, want_x=False, gather=False, optimistic=True, skip_sweep=True)
-        for _ in range(3):
-            step12()
-        barrier()
-        b0_, b1_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        b0_.record()
-        for _ in range(args.steps):
-            step12()
-        b1_.record()
-        barrier()
-        tb = torch.tensor([b0_.elapsed_time(b1_) / args.steps], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(tb, op=dist.ReduceOp.MAX)
-        bp_alone_ms = float(tb.item())
-        path._graph = None                                    # the next step_graph call re-captures the full step
+        bp_alone_ms, _, _ = timed(step12, args.steps, 3)
+        path.drop_graph()
     except Exception as exc:                                  # pragma: no cover - reported, not fatal
         bp_alone_ms = None
         print(f"bench: stage-1/2 timing failed: {exc!r}", file=sys.stderr)
 
-    # ---- stages 1+2 inside the timed step against their composite roofline: per kernel
+    # ---- stages 1+2 against their composite roofline: per kernel
     #      max(algorithmic bytes / measured HBM peak, flops / measured FP64 peak), complex128 operands, real operator values
     sweep_ms_alone = kernels.get("sweep_lu_gsm", {}).get("ms_per_step")
     bp_roof = None
     if sweep_ms_alone:
-        n_loc, r_ = n // world, wl["r"]
+        n_loc = n / world
         wbytes = 16.0 if not real else 8.0
         fl = 1.0 if not real else 0.25                            # real twins: a quarter of the flops
-        bw, p64 = hbm_peak * 1e9, FP64_PEAK_TFLOPS * 1e12
-        t_roof = max(6 * wbytes * n_loc * r_ / bw, 20.0 * n_loc * r_ * r_ * fl / p64)                       # CholeskyQR2 + rotation
+        bw, p64 = hbm_peak * 1e9, fp64_peak * 1e12
+        t_roof = max(6 * wbytes * n_loc * r / bw, 20.0 * n_loc * r * r * fl / p64)                       # CholeskyQR2 + rotation
         for a_ in (in_c, in_gamma):
             nnz_loc = a_.nnz / world
-            t_roof += max((nnz_loc * 12.0 + 4.0 * (n_loc + 1) + 2 * wbytes * n_loc * r_) / bw, (2.0 if real else 4.0) * nnz_loc * r_ / p64)   # SpMM (real operator values)
-            t_roof += max((2 * wbytes * n_loc * r_ + wbytes * r_ * r_) / bw, 8.0 * n_loc * r_ * r_ * fl / p64)     # Q^T (A Q)
+            t_roof += max((nnz_loc * 12.0 + 4.0 * (n_loc + 1) + 2 * wbytes * n_loc * r) / bw, (2.0 if real else 4.0) * nnz_loc * r / p64)   # SpMM (real operator values)
+            t_roof += max((2 * wbytes * n_loc * r + wbytes * r * r) / bw, 8.0 * n_loc * r * r * fl / p64)     # Q^T (A Q)
         bp_ms = ms_step - sweep_ms_alone - stage_ms["gather"]
         bp_roof = {"ms": bp_alone_ms, "t_roof_ms": t_roof * 1e3, "frac": t_roof * 1e3 / bp_alone_ms if bp_alone_ms else None,
                    "ms_in_step": bp_ms, "frac_in_step": t_roof * 1e3 / bp_ms if bp_ms > 0 else None,
-                   "note": "ms: stages 1+2 timed alone on the device (max over ranks; N=1: their own CUDA graph); ms_in_step: whole timed step minus "
+                   "note": "ms: stages 1+2 timed alone on the device (max over ranks); ms_in_step: whole timed step minus "
                            "the sweep kernel timed alone; roofline = sum over kernels of max(bytes/HBM, flops/FP64) per GPU (SURVEY 8d)"}
+
+    # ---- secondary line: BASELINE configs[1] (N=200k, r=64, 2 ports, 10k points), same timed loop, single GPU only
+    secondary = None
+    if world == 1 and name != "cfg2" and not args.no_secondary:
+        del path, s_dev
+        torch.cuda.empty_cache()
+        wl2 = WORKLOADS["cfg2"]
+        ops2 = build_operators(wl2)
+        path2 = make_path(ops2, 0, 1)
+        s2 = dv.real_or_complex_to_device(snapshot_rows(ops2[4], wl2["r"], 0, ops2[4]), dev, widen=not real)
+
+        def step2():
+            return path2.step_graph(s2, want_x=False) if use_graph else path2.step_deferred(s2, want_x=False, gather=True)
+        ms2, out2, _ = timed(step2, max(args.steps, 20), 3)
+        ok2 = (path2.verify() is None) if use_graph else path2.verify_deferred()
+        idx2 = sample_indices(wl2["f"], 256)
+        red2 = [np.zeros((wl2["r"], wl2["r"])) if o is None else np.ascontiguousarray(o.cpu().numpy().real) for o in out2[2][:3]]
+        red2.append(np.ascontiguousarray(out2[2][3].cpu().numpy().real))
+        g2, _ = cpu_sweep(ops2[3][idx2], red2)
+        e2 = per_point_rel(out2[0][torch.from_numpy(idx2).to(dev)].cpu().numpy(), g2)
+        tol2 = np.maximum(1e-10, 20 * EPS * system_conds(ops2[3][idx2], red2))
+        secondary = {"cfg2": {"config": workload_config("cfg2", wl2, ops2[4]), "value": wl2["f"] / (ms2 * 1e-3), "unit": UNIT, "ms_per_step": ms2,
+                              "dtype": "c128" if not real else "f64", "cholqr2_flags_ok": bool(ok2),
+                              "parity_stage_isolated": {"max_rel_err": float(e2.max()), "worst_err_over_tol": float((e2 / tol2).max()), "points": int(idx2.size)}}}
 
     if rank == 0:
         sweep_k = kernels.get("sweep_lu_gsm", {})
-        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        cfg = workload_config(name, wl, n)
+        cfg.update({"N_dof_per_gpu": n // world, "step": "basis (CholeskyQR2+SVD) + projection + reduced solves + S-parameters" +
+                    (", replayed from one CUDA graph" if use_graph else ", eager launches"),
+                    "parallelism": "rows of Q/operators and sweep points block-sharded over %d GPU(s)" % world})
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warm,
+                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "c128" if not real else "f64", "data": "synthetic",
-                "config": {"workload": args.workload + ": " + wl["desc"], "N_dof_per_gpu": n // world, "N_dof_total": n, "r": wl["r"], "ports": wl["m"],
-                           "freq_points_total": f_total, "step": "basis (CholeskyQR2+SVD) + projection + reduced solves + S-parameters" + (", replayed from one CUDA graph" if use_graph else ""),
-                           "l2": "inputs larger than L2 (snapshot block %.0f MB + operators per GPU); no flush" % (s_dev.numel() * s_dev.element_size() / 1e6),
-                           "parallelism": "rows of Q/operators and sweep points block-sharded over %d GPU(s)" % world},
-                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu_baseline,
+                "config": cfg,
+                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu_baseline, "parity": parity,
                 "other_dtype": alt,
                 "basis_plus_projection": bp_roof,
                 "stages": {"basis_plus_projection_ms": stage_ms["basis_plus_projection"], "sweep_ms": stage_ms["sweep"],
                            "gather_ms": stage_ms["gather"],
                            "sweep_kernel_points_per_s_per_gpu": (f_total / world) / (sweep_k["ms_per_step"] * 1e-3) if sweep_k.get("ms_per_step") else None},
-                "kernels": kernels}
+                "kernels": kernels, "secondary": secondary}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -506,31 +690,33 @@ def run_b200(args, wl, rank, world, local_rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
-    ap.add_argument("--cpu-points", type=int, default=2000, help="sweep points the CPU arm solves per step (scaled to the full axis)")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
+    ap.add_argument("--cpu-points", type=int, default=0, help="sweep points the CPU legs solve (scaled to the full axis); 0 = per workload")
+    ap.add_argument("--cpu-rows", type=int, default=62500, help="rows of the snapshot block / operators the reference arm's stages 1+2 run on per step")
+    ap.add_argument("--parity", default="auto", choices=["auto", "full", "isolated"],
+                    help="full: the whole path on the CPU once (svd of the full snapshot block: ~30 s at cfg3) -- default at N=1; "
+                         "isolated: CPU sweep on the reduced model the GPU produced")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the cfg2 line reported under 'secondary'")
     ap.add_argument("--dtype", default="c128", choices=["auto", "c128", "f64"],
                     help="c128: complex128 kernels throughout (north star); f64: the real float64 twins (the reference's own dtype; "
                          "valid because the synthetic operators and snapshots are real, like the reference's data)")
     ap.add_argument("--no-alt-dtype", action="store_true", help="skip the second timed loop on the other arithmetic type")
-    ap.add_argument("--no-graph", action="store_true", help="run the eager (adaptive CholeskyQR) step instead of the CUDA-graph replay at N=1")
+    ap.add_argument("--no-graph", action="store_true", help="run the eager (adaptive CholeskyQR) step instead of the CUDA-graph replay")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
-        run_reference(args, wl, rank, world)
+        run_reference(args, args.workload, wl, rank, world)
         return
     if world != args.gpus:
-        if args.gpus == 1 and world == 1:
-            pass
-        else:
-            raise SystemExit(f"bench.py: --gpus {args.gpus} needs torchrun with {args.gpus} ranks (WORLD_SIZE={world})")
-    run_b200(args, wl, rank, world, local_rank)
+        raise SystemExit(f"bench.py: --gpus {args.gpus} needs torchrun with {args.gpus} ranks (WORLD_SIZE={world})")
+    run_b200(args, args.workload, wl, rank, world, local_rank)
 
 
 if __name__ == "__main__":

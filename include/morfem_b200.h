@@ -190,6 +190,12 @@ int mf_estimator_c128(const mf_c128* X, int r, int m, int64_t F, const mf_c128* 
                       const double* c0, const double* c1, const double* c2, const double* cb,
                       double* err, void* stream);
 
+/* ---- measurement helper (bench.py, SURVEY 8d: "FP64 peak must be measured on the box") ---------------------
+ * FP64 tensor-pipe (DMMA m8n8k4) issue rate of the current device in TFLOP/s, best of four timed launches of an
+ * issue-loop kernel (8 independent accumulators per warp, `iters` rounds).  The one entry point that BLOCKS and
+ * allocates (a few KB, freed before return): it times itself with CUDA events on `stream`. */
+int mf_peak_dmma_tflops(int iters, double* tflops_host, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -70,6 +70,7 @@ SIGNATURES = {
                                      c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
                                      c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_size_t, c_void_p]),
     "mf_gsm_c128": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
+    "mf_peak_dmma_tflops": (c_int, [c_int, c_void_p, c_void_p]),
     "mf_estimator_c128": (c_int, [c_void_p, c_int, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
                                   c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
 }

@@ -83,17 +83,28 @@ class _Workspaces:
 
     def __init__(self):
         self._bufs = {}
+        self._pinned = set()       # keys whose current buffer is referenced by a captured CUDA graph
+        self._retired = []         # outgrown buffers that a graph may still replay into
 
     def get(self, key: str, nbytes: int, device) -> torch.Tensor:
         k = (key, str(device))
         buf = self._bufs.get(k)
         if buf is None or buf.numel() < nbytes:
+            if buf is not None and k in self._pinned:
+                self._retired.append(buf)          # a graph holds its raw pointer: keep the memory alive
+                self._pinned.discard(k)
             buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
             self._bufs[k] = buf
         return buf
 
+    def pin_all(self):
+        """Called after a CUDA-graph capture: every buffer handed out so far may be baked into the graph."""
+        self._pinned.update(self._bufs.keys())
+
     def clear(self):
         self._bufs.clear()
+        self._pinned.clear()
+        self._retired.clear()
 
 
 workspaces = _Workspaces()
@@ -481,6 +492,8 @@ class BasisInfo:
         self._sweeps = jacobi_sweeps   # device tensor or int
         self.kept = kept               # columns kept after truncation
         self.flags = None              # optimistic CholeskyQR2: device flag blocks awaiting verification
+        self.q_ready = None            # basis_and_projection(defer_q=True): event to wait for before q is used
+        self.keepalive = None          # ... and the operands of the side-stream product, released after that wait
 
     @property
     def sigma(self) -> np.ndarray:
@@ -764,8 +777,13 @@ def basis_and_projection(s: torch.Tensor, project_block, group=None, truncation_
     b_r = gemm_tn(w, bt, conj=False)
     info.flags = cq.flags            # None unless optimistic: the caller verifies with flags_ok(flags.cpu())
     info.q_ready = None
+    info.keepalive = None
     if defer_q and want_q:
         info.q_ready = ev1           # the caller joins: current_stream().wait_event(info.q_ready)
+        # the side stream is still reading the un-rotated block (cq.x, allocated on the main stream) when this function
+        # returns: keep it referenced until the caller has joined, otherwise the caching allocator may hand its memory to
+        # the next main-stream allocation (the sweep outputs) while `q = x w` is in flight -- also inside a captured graph
+        info.keepalive = cq
     else:
         main.wait_event(ev1)
     return q, reduced, b_r, info

@@ -126,6 +126,65 @@ def exchange_halo(q_local: torch.Tensor, plan: HaloPlan, out: Optional[torch.Ten
     return win
 
 
+def slab_halo_rows(rank_windows: List[Tuple[int, int]], owned: List[Tuple[int, int]]) -> Optional[int]:
+    """Slab height H for the all-gather halo exchange, or None when point-to-point messages are needed.
+
+    Every rank publishes its top H and bottom H local rows; the exchange works when every row a rank needs from a peer
+    lies inside one of that peer's two slabs (banded operators: the window reaches a few hundred rows into the
+    neighbouring blocks) and every rank owns at least H rows."""
+    world = len(owned)
+    h = 0
+    for p in range(world):
+        (w0, w1), (r0, r1) = rank_windows[p], owned[p]
+        h = max(h, r0 - w0, w1 - r1)
+    if h == 0:
+        return 0
+    if any(hi - lo < h for lo, hi in owned):
+        return None
+    for p in range(world):
+        w0, w1 = rank_windows[p]
+        for q in range(world):
+            if q == p:
+                continue
+            lo, hi = max(w0, owned[q][0]), min(w1, owned[q][1])
+            if hi <= lo:
+                continue
+            in_top = hi <= owned[q][0] + h
+            in_bottom = lo >= owned[q][1] - h
+            if not (in_top or in_bottom):
+                return None
+    return h
+
+
+def exchange_halo_slabs(q_local: torch.Tensor, plan: HaloPlan, h: int, owned: List[Tuple[int, int]],
+                        out: Optional[torch.Tensor] = None, group=None) -> torch.Tensor:
+    """Same result as ``exchange_halo`` with ONE fixed-size collective: every rank contributes its top and bottom ``h`` rows
+    to an all-gather, the window is assembled from the peers' slabs with device copies.  Unlike the point-to-point version
+    this is a plain NCCL collective on static shapes, so a CUDA graph can capture the whole multi-rank step."""
+    r = q_local.shape[1]
+    nwin = plan.win1 - plan.win0
+    if out is None or out.shape[0] < nwin or out.shape[1] != r or out.dtype != q_local.dtype or out.device != q_local.device:
+        out = torch.empty((nwin, r), dtype=q_local.dtype, device=q_local.device)
+    win = out[:nwin]
+    win[plan.row0 - plan.win0:plan.row1 - plan.win0].copy_(q_local)
+    if h == 0:                                             # no rank needs a remote row (all ranks agree on h)
+        return win
+    slab = torch.empty((2 * h, r), dtype=q_local.dtype, device=q_local.device)
+    slab[:h].copy_(q_local[:h])
+    slab[h:].copy_(q_local[q_local.shape[0] - h:])
+    gathered = torch.empty((plan.world * 2 * h, r), dtype=q_local.dtype, device=q_local.device)   # rank p's slabs at rows 2 h p ..
+    dist.all_gather_into_tensor(_as_real(gathered), _as_real(slab), group=group)
+    for peer, lo, hi in plan.recv:
+        p0, p1 = owned[peer]
+        base = 2 * h * peer
+        if hi <= p0 + h:                                   # inside the peer's top slab (rows p0 .. p0 + h)
+            src = gathered[base + lo - p0:base + hi - p0]
+        else:                                              # inside its bottom slab (rows p1 - h .. p1)
+            src = gathered[base + h + lo - (p1 - h):base + h + hi - (p1 - h)]
+        win[lo - plan.win0:hi - plan.win0].copy_(src)
+    return win
+
+
 def gather_points(local: torch.Tensor, f_total: int, group=None) -> torch.Tensor:
     """All-gather of per-point results split with ``even_split``: returns the (f_total, ...) tensor on every rank."""
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
@@ -165,6 +224,7 @@ class ShardedHotPath:
         self.f0, self.f1 = even_split(f_total, self.world, self.rank)
         self.ops = []
         self.plans = []
+        self._windows = {}
         for a in operators:
             if a is None or a.nnz == 0:
                 self.ops.append(None)
@@ -173,9 +233,26 @@ class ShardedHotPath:
             window = column_window(np.asarray(a.indptr), np.asarray(a.indices), self.row0, self.row1, a.shape[0])
             windows = gather_windows(window, group) if self.world > 1 else [window]
             plan = build_halo_plan(self.rank, self.world, n_rows, windows)
+            self._windows[id(plan)] = windows
             csr = dv.csr_of_transpose(a, self.dev, row_range=(self.row0, self.row1), col_offset=plan.win0)   # window-relative columns
             self.ops.append(csr)
             self.plans.append(plan)
+        # halo exchange: one slab all-gather (capturable by a CUDA graph) when every halo row sits within H rows of a block
+        # boundary -- the banded FEM case; point-to-point messages otherwise
+        self.owned = owner_ranges(n_rows, self.world)
+        self.halo_h = 0
+        self.halo_mode = "none"
+        if self.world > 1:
+            hs = []
+            for a, plan in zip(operators, self.plans):
+                if plan is None:
+                    continue
+                hs.append(slab_halo_rows(self._windows[id(plan)], self.owned))
+            if any(h is None for h in hs):
+                self.halo_mode = "p2p"
+            else:
+                self.halo_h = max(hs) if hs else 0
+                self.halo_mode = "allgather"
         # operators with one sparsity pattern (Ct and Tt of a FEM model) are multiplied in one pass (device.spmm2)
         live = [i for i, c in enumerate(self.ops) if c is not None]
         self.pair = None
@@ -192,6 +269,21 @@ class ShardedHotPath:
         self._pending = []           # device flag blocks of step_deferred calls awaiting verify_deferred
 
 
+    @property
+    def graph_capable(self) -> bool:
+        """True when ``step_graph`` can capture this rank's step (single rank, or a multi-rank step whose exchanges are
+        all capturable NCCL collectives)."""
+        return self.world == 1 or self.halo_mode == "allgather"
+
+    def drop_graph(self) -> None:
+        """Forget the captured step (its static outputs stay valid for whoever still references them)."""
+        self._graph = None
+
+    def _exchange(self, x: torch.Tensor, plan: HaloPlan, buf: Optional[torch.Tensor], group) -> torch.Tensor:
+        if self.halo_mode == "allgather":
+            return exchange_halo_slabs(x, plan, self.halo_h, self.owned, buf, group)
+        return exchange_halo(x, plan, buf, group)
+
     def _mark(self, ev):
         if ev is not None:
             e = torch.cuda.Event(enable_timing=True)
@@ -205,20 +297,27 @@ class ShardedHotPath:
         the ~45 short kernels of a step.  Call ``verify()`` before trusting the results: if a Cholesky broke down or the
         block needed a third pass it re-runs the adaptive ``step``.  Outputs are static tensors overwritten by the next
         replay.  ``skip_sweep`` captures stages 1 + 2 only (bench.py times the basis + projection stage with it)."""
-        if self.world > 1:
-            raise RuntimeError("step_graph is single-rank; use step() under torchrun")
+        if not self.graph_capable:
+            raise RuntimeError("step_graph: this rank's halo exchange needs point-to-point messages, which a CUDA graph cannot "
+                               "capture; use step() / step_deferred()")
+        gather = self.world > 1 and not skip_sweep
         key = (tuple(s_local.shape), s_local.dtype, bool(want_x), bool(skip_sweep))
         if self._graph is None or self._graph["key"] != key:
             static_s = s_local.clone()
-            for _ in range(2):                                   # warm-up: workspaces, function attributes, side stream
-                self.step(static_s, want_x=want_x, gather=False, optimistic=True, skip_sweep=skip_sweep)
+            for _ in range(2):                                   # warm-up: workspaces, function attributes, side stream, NCCL
+                self.step(static_s, want_x=want_x, gather=gather, optimistic=True, skip_sweep=skip_sweep)
             torch.cuda.synchronize()
+            if self.world > 1:
+                dist.barrier(group=self.group)
+                torch.cuda.synchronize()
             from . import _ffi
             graph = torch.cuda.CUDAGraph()
             launches0 = _ffi.launch_count()
-            with torch.cuda.graph(graph):
-                out = self.step(static_s, want_x=want_x, gather=False, optimistic=True, skip_sweep=skip_sweep)
+            # thread_local: NCCL's watchdog thread may touch the CUDA API while this thread captures
+            with torch.cuda.graph(graph, capture_error_mode="thread_local" if self.world > 1 else "global"):
+                out = self.step(static_s, want_x=want_x, gather=gather, optimistic=True, skip_sweep=skip_sweep)
             self.launches_per_graph = _ffi.launch_count() - launches0     # kernels of this library inside one replay
+            self.dv.workspaces.pin_all()           # the replay writes into the workspace buffers captured here
             flags_host = torch.empty((2, 32), dtype=torch.uint8).pin_memory()
             self._graph = {"key": key, "graph": graph, "s": static_s, "out": out, "flags_host": flags_host, "want_x": want_x}
         gr = self._graph
@@ -251,7 +350,7 @@ class ShardedHotPath:
         torch.cuda.current_stream().synchronize()
         if self.dv.flags_ok(gr["flags_host"]):
             return None
-        return self.step(gr["s"], want_x=gr["want_x"], gather=False)
+        return self.step(gr["s"], want_x=gr["want_x"], gather=self.world > 1)
 
     def step(self, s_local: torch.Tensor, want_x: bool = False, gather: bool = True, optimistic: bool = False, skip_sweep: bool = False):
         """One pass of the hot path.  Returns (gsm_all or gsm_local, q_local, (a0_r, a1_r, a2_r, b_r), sweep result)
@@ -275,7 +374,7 @@ class ShardedHotPath:
                 plan = self.plans[i0]
                 xin = x
                 if self.world > 1:
-                    self._win = exchange_halo(x, plan, self._win, group)
+                    self._win = self._exchange(x, plan, self._win, group)
                     xin = self._win[:plan.win1 - plan.win0]
                 y0, y1 = dv.spmm2(self.ops[i0], self.ops[i1], xin)
                 for k, (i, y) in enumerate(((i0, y0), (i1, y1))):
@@ -287,7 +386,7 @@ class ShardedHotPath:
                 if self.world > 1:
                     key = (plan.win0, plan.win1, tuple(plan.send), tuple(plan.recv))
                     if key not in windows:
-                        windows[key] = exchange_halo(x, plan, self._win if not windows else None, group)
+                        windows[key] = self._exchange(x, plan, self._win if not windows else None, group)
                         if len(windows) == 1:
                             self._win = windows[key]
                     y = dv.spmm(csr, windows[key][:plan.win1 - plan.win0])
@@ -308,6 +407,7 @@ class ShardedHotPath:
             if info.q_ready is not None:
                 torch.cuda.current_stream().wait_event(info.q_ready)
                 info.q_ready = None
+            info.keepalive = None        # the side stream has been joined: the un-rotated block may be reused now
 
         if skip_sweep:                       # stages 1 + 2 only (timing of the basis + projection stage)
             join_q()

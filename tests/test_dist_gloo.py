@@ -68,6 +68,13 @@ def _worker(rank, world, port, n_grid, r, f_total, out_dir):
         plan = mfd.build_halo_plan(rank, world, n, mfd.gather_windows(window))
         win = mfd.exchange_halo(s_loc, plan)
         assert np.array_equal(win.numpy(), s[plan.win0:plan.win1])
+        # the same window through the slab all-gather (the exchange a CUDA graph can capture)
+        windows = mfd.gather_windows(window)
+        owned = mfd.owner_ranges(n, world)
+        h = mfd.slab_halo_rows(windows, owned)
+        assert h is not None and 0 < h <= 3 * 2 + 3 + 1
+        win2 = mfd.exchange_halo_slabs(s_loc, plan, h, owned)
+        assert np.array_equal(win2.numpy(), s[plan.win0:plan.win1])
         at = ct.T.tocsr()
         y_loc = at[row0:row1, plan.win0:plan.win1] @ win.numpy()
         a_r = torch.from_numpy(y_loc.T @ s[row0:row1])
@@ -103,3 +110,18 @@ def test_halo_window_buffer_is_not_reused_across_dtypes():
     win_r = mfd.exchange_halo(qr, plan, out=win_c)
     assert win_r.dtype == torch.float64 and torch.equal(win_r, qr)
     assert torch.equal(mfd.exchange_halo(qc, plan, out=win_c), qc)
+
+
+def test_slab_halo_rows_modes():
+    """H = deepest reach of any window into a neighbouring block; None (point-to-point needed) when a window reaches past a
+    neighbour's slab or a rank owns fewer than H rows."""
+    owned = mfd.owner_ranges(100, 4)                       # 25 rows each
+    assert mfd.slab_halo_rows([(0, 25), (25, 50), (50, 75), (75, 100)], owned) == 0
+    assert mfd.slab_halo_rows([(0, 30), (20, 55), (45, 80), (70, 100)], owned) == 5
+    assert mfd.slab_halo_rows([(0, 60), (25, 50), (50, 75), (75, 100)], owned) is None      # rank 0 needs rows of rank 2: 35 > 25 owned
+    owned = mfd.owner_ranges(100, 2)
+    # rank 0's window reaches 30 rows into rank 1's block: one slab of 30 rows covers it
+    assert mfd.slab_halo_rows([(0, 80), (40, 100)], owned) == 30
+    # a window that skips over a whole neighbouring block needs rows from the middle of a far block
+    owned = mfd.owner_ranges(90, 3)
+    assert mfd.slab_halo_rows([(0, 70), (30, 60), (60, 90)], owned) is None
