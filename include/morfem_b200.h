@@ -135,13 +135,17 @@ int mf_spmm_csr_f64(const int32_t* rowptr, const int32_t* colidx, const double* 
                     const double* Q, int64_t ldq, int r, double* Y, int64_t ldy, void* stream);
 int mf_spmm_grouped_f64(const int64_t* ustart, const int32_t* ucols, const double* uvals, int64_t nrows, int G,
                         const double* Q, int64_t ldq, int r, double* Y, int64_t ldy, void* stream);
-/* Batched reduced sweep on REAL reduced operators (same semantics as mf_sweep_lu_gsm_c128; X is real, S complex).
- * Shared-memory-resident blocked kernel only: mf_sweep_f64_supported(r, m) tells whether (r, m) fits (r <= 128);
- * otherwise widen the operands and call the complex128 entry. */
+/* Batched reduced sweep on REAL reduced operators (same semantics as mf_sweep_lu_gsm_c128; X is real, S complex) -- the
+ * reference's own arithmetic (implementation.py:190 allocates a float64 result; lu_factor / lu_solve on float64, :477-478).
+ * variant 0 = auto (matrix resident in shared memory up to r = 128, the left-looking streamed LU of sweep_left.cu up to
+ * r = 512), 3 / 5 force one of the two.  mf_sweep_f64_supported(r, m): any variant handles (r, m); workspace from
+ * mf_sweep_f64_ws_bytes (the shared-memory kernel needs none). */
 int mf_sweep_f64_supported(int r, int m);
+int mf_sweep_f64_variant_supported(int r, int m, int variant);
+size_t mf_sweep_f64_ws_bytes(int r, int m, int64_t F, int variant);
 int mf_sweep_lu_gsm_f64(const double* A0, const double* A1, const double* A2, int64_t lda, const double* Br, int64_t ldb, int r, int m,
                         const double* c0, const double* c1, const double* c2, const double* cb, const double* zscale, int64_t F,
-                        double* X, mf_c128* S, int* info, void* stream);
+                        double* X, mf_c128* S, int* info, int variant, void* ws, size_t ws_bytes, void* stream);
 /* One-sided Jacobi SVD of a REAL r x r matrix (r <= 64, see mf_jacobi_svd_f64_supported); X is not modified. */
 int mf_jacobi_svd_f64_supported(int r);
 int mf_jacobi_svd_f64(const double* X, int64_t ld, int r, double* U, int64_t ldu, double* sigma, int max_sweeps,

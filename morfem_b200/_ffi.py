@@ -57,8 +57,11 @@ SIGNATURES = {
     "mf_spmm_csr_f64": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int, c_void_p, c_int64, c_void_p]),
     "mf_spmm_grouped_f64": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_int64, c_int, c_void_p, c_int64, c_void_p]),
     "mf_sweep_f64_supported": (c_int, [c_int, c_int]),
+    "mf_sweep_f64_variant_supported": (c_int, [c_int, c_int, c_int]),
+    "mf_sweep_f64_ws_bytes": (c_size_t, [c_int, c_int, c_int64, c_int]),
     "mf_sweep_lu_gsm_f64": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int,
-                                    c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
+                                    c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p,
+                                    c_int, c_void_p, c_size_t, c_void_p]),
     "mf_jacobi_svd_f64_supported": (c_int, [c_int]),
     "mf_jacobi_svd_f64": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int64, c_void_p, c_int, c_double, c_void_p, c_void_p]),
     "mf_project_rhs_f64": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int64, c_int, c_int64, c_int64, c_void_p, c_int64,

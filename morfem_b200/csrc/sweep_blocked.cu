@@ -341,24 +341,19 @@ int launch_blocked(const SweepParams& p, const BlockedGeom& gm, cudaStream_t str
 
 }  // namespace
 
-// sweep_stream.cu: the same algorithm with the matrix streamed from an L2-resident workspace (r up to 512)
-bool sweep_stream_supports(int r, int m);
-size_t sweep_stream_ws_bytes(int r, int m, long long F);
-int sweep_stream_launch(const SweepParams& p, size_t ws_bytes, cudaStream_t stream);
-
-static bool blocked_fits_smem(int r, int m) {
+bool sweep_blocked_fits_smem(int r, int m) {
     if (r < 1 || m < 1 || m > MF_MAX_PORTS) return false;
     const BlockedGeom gm = blocked_geom(r, m);
     return gm.R <= 128 && gm.smem <= 226 * 1024;
 }
 
-bool sweep_blocked_supports(int r, int m) { return blocked_fits_smem(r, m) || sweep_stream_supports(r, m); }
+bool sweep_blocked_supports(int r, int m) { return sweep_blocked_fits_smem(r, m); }
 
-size_t sweep_blocked_ws_bytes(int r, int m, long long F) { return blocked_fits_smem(r, m) ? 0 : sweep_stream_ws_bytes(r, m, F); }
+size_t sweep_blocked_ws_bytes(int, int, long long) { return 0; }
 
 int sweep_blocked_launch(const SweepParams& p_in, size_t ws_bytes, cudaStream_t stream) {
     SweepParams p = p_in;
-    if (!blocked_fits_smem(p.r, p.m) || getenv("MF_SWEEP_FORCE_STREAM")) return sweep_stream_launch(p, ws_bytes, stream);
+    if (!sweep_blocked_fits_smem(p.r, p.m)) MF_FAIL_ARG(7, "matrix does not fit in shared memory (use the left-looking variant)");
     const BlockedGeom gm = blocked_geom(p.r, p.m);
 #ifdef MF_BLOCKED_DEBUG
     if (getenv("MF_BLOCKED_DUMP") && p.ws && ws_bytes >= sizeof(cplx) * gm.R * gm.NCB * 8) p.ws_stride = -12345;

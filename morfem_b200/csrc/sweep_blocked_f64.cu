@@ -3,6 +3,7 @@
 // memory per point (36 KiB at r = 64: up to six points in flight per SM instead of three), a quarter of the flops, and
 // results bit-identical to the complex128 kernel (whose imaginary parts would all be exact zeros).  Same algorithm,
 // schedule and storage scheme; see sweep_blocked.cu for the description.  The S-parameters stay complex: Z = j zs x^T b.
+#include <stdlib.h>
 #include "sweep_common.cuh"
 
 namespace {
@@ -381,31 +382,65 @@ int rlaunch(const SweepParamsR& p, const RGeom& gm, cudaStream_t stream) {
 
 }  // namespace
 
-extern "C" int mf_sweep_f64_supported(int r, int m) {
-    if (r < 1 || m < 1 || m > MF_MAX_PORTS) return 0;
+// sweep_left.cu: the left-looking streamed LU on float64 elements (matrices that do not fit in shared memory, r up to 512)
+bool sweep_left_supports_f64(int r, int m);
+size_t sweep_left_ws_bytes_f64(int r, int m, long long F);
+int sweep_left_launch_f64(const double* A0, const double* A1, const double* A2, long long lda, const double* Br, long long ldb, int r, int m,
+                          const double* c0, const double* c1, const double* c2, const double* cb, const double* zs, long long F,
+                          double* X, cplx* S, int* info, void* ws, size_t ws_bytes, cudaStream_t stream);
+
+static bool rblocked_fits(int r, int m) {
+    if (r < 1 || m < 1 || m > MF_MAX_PORTS) return false;
     const RGeom gm = rgeom(r, m);
-    return (gm.R <= 128 && gm.smem <= 226 * 1024) ? 1 : 0;
+    return gm.R <= 128 && gm.smem <= 226 * 1024;
+}
+
+static bool f64_uses_left(int r, int m, int variant) {
+    if (variant == 5) return true;
+    if (variant == 3) return false;
+    return !rblocked_fits(r, m) || (getenv("MF_SWEEP_FORCE_LEFT") && sweep_left_supports_f64(r, m));
+}
+
+extern "C" int mf_sweep_f64_supported(int r, int m) {
+    return (rblocked_fits(r, m) || sweep_left_supports_f64(r, m)) ? 1 : 0;
+}
+
+extern "C" int mf_sweep_f64_variant_supported(int r, int m, int variant) {
+    if (variant == 0) return mf_sweep_f64_supported(r, m);
+    if (variant == 3) return rblocked_fits(r, m) ? 1 : 0;
+    if (variant == 5) return sweep_left_supports_f64(r, m) ? 1 : 0;
+    return 0;
+}
+
+extern "C" size_t mf_sweep_f64_ws_bytes(int r, int m, int64_t F, int variant) {
+    if (r <= 0 || m <= 0 || F <= 0 || !mf_sweep_f64_variant_supported(r, m, variant)) return 256;
+    const size_t need = f64_uses_left(r, m, variant) ? sweep_left_ws_bytes_f64(r, m, F) : 0;
+    return need < 256 ? 256 : need;
 }
 
 extern "C" int mf_sweep_lu_gsm_f64(const double* A0, const double* A1, const double* A2, int64_t lda,
                                    const double* Br, int64_t ldb, int r, int m,
                                    const double* c0, const double* c1, const double* c2, const double* cb,
-                                   const double* zscale, int64_t F, double* X, mf_c128* S, int* info, void* stream) {
+                                   const double* zscale, int64_t F, double* X, mf_c128* S, int* info, int variant,
+                                   void* ws, size_t ws_bytes, void* stream) {
     if (!A0 && !A1 && !A2) MF_FAIL_ARG(1, "all three operators are NULL");
     if (lda < r) MF_FAIL_ARG(4, "lda < r");
     if (!Br || ldb < m) MF_FAIL_ARG(5, "Br is NULL or ldb < m");
-    if (!mf_sweep_f64_supported(r, m)) MF_FAIL_ARG(7, "(r, m) not supported by the real sweep (mf_sweep_f64_supported): use the complex128 entry");
+    if (variant != 0 && variant != 3 && variant != 5) MF_FAIL_ARG(18, "variant must be 0 (auto), 3 (shared-memory blocked) or 5 (left-looking)");
+    if (!mf_sweep_f64_variant_supported(r, m, variant)) MF_FAIL_ARG(7, "(r, m) not supported by this variant of the real sweep (mf_sweep_f64_variant_supported): use the complex128 entry");
     if (!c0 || !c1 || !c2) MF_FAIL_ARG(9, "coefficient arrays must not be NULL");
     if (!cb) MF_FAIL_ARG(12, "cb is NULL");
     if (S && !zscale) MF_FAIL_ARG(13, "zscale is NULL but S is requested");
     if (F < 0) MF_FAIL_ARG(14, "F < 0");
     if (!X && !S) MF_FAIL_ARG(15, "neither X nor S requested");
     if (F == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (f64_uses_left(r, m, variant))
+        return sweep_left_launch_f64(A0, A1, A2, lda, Br, ldb, r, m, c0, c1, c2, cb, zscale, F, X, (cplx*)S, info, ws, ws_bytes, st);
     SweepParamsR p;
     p.A0 = A0; p.A1 = A1; p.A2 = A2; p.lda = lda; p.Br = Br; p.ldb = ldb; p.r = r; p.m = m;
     p.c0 = c0; p.c1 = c1; p.c2 = c2; p.cb = cb; p.zs = zscale; p.F = F; p.X = X; p.S = (cplx*)S; p.info = info;
     const RGeom gm = rgeom(r, m);
-    cudaStream_t st = (cudaStream_t)stream;
     if (gm.R <= 32) return rlaunch<1, 2, 12>(p, gm, st);
     if (gm.R <= 64) return rlaunch<2, 4, 5>(p, gm, st);
     if (gm.R <= 96) return rlaunch<3, 8, 2>(p, gm, st);

@@ -815,8 +815,8 @@ def sweep(a0s: Optional[torch.Tensor], a1s: Optional[torch.Tensor], a2s: Optiona
     _check_mat(br, "br")
     r, m = br.shape
     if all(o.dtype == F64 for o in ops) and br.dtype == F64:
-        if variant in (0, 3) and lib.mf_sweep_f64_supported(r, m):
-            return _sweep_f64(lib, a0s, a1s, a2s, br, c0, c1, c2, cb, zscale, want_x, want_gsm)
+        if variant in (0, 3, 5) and lib.mf_sweep_f64_variant_supported(r, m, variant):
+            return _sweep_f64(lib, a0s, a1s, a2s, br, c0, c1, c2, cb, zscale, want_x, want_gsm, variant)
         a0s, a1s, a2s = (None if o is None else o.to(C128) for o in (a0s, a1s, a2s))     # no real kernel for this shape
         br = br.to(C128)
         ops = [o for o in (a0s, a1s, a2s) if o is not None]
@@ -845,8 +845,8 @@ def sweep(a0s: Optional[torch.Tensor], a1s: Optional[torch.Tensor], a2s: Optiona
     return SweepResult(x, gsm, info)
 
 
-def _sweep_f64(lib, a0s, a1s, a2s, br, c0, c1, c2, cb, zscale, want_x, want_gsm) -> SweepResult:
-    """Real reduced model: the float64 twin of the blocked kernel (half the shared memory, a quarter of the flops)."""
+def _sweep_f64(lib, a0s, a1s, a2s, br, c0, c1, c2, cb, zscale, want_x, want_gsm, variant=0) -> SweepResult:
+    """Real reduced model: the float64 twins of the blocked kernels (half the bytes, a quarter of the flops)."""
     ops = [o for o in (a0s, a1s, a2s) if o is not None]
     r, m = br.shape
     lda = ops[0].stride(0)
@@ -859,9 +859,12 @@ def _sweep_f64(lib, a0s, a1s, a2s, br, c0, c1, c2, cb, zscale, want_x, want_gsm)
     info = torch.zeros(nf, dtype=torch.int32, device=dev)
     flops_pt = (2.0 / 3.0) * r ** 3 + 2.0 * r * r * m + 4.0 * r * r + 2.0 * r * m * m
     bytes_pt = 16.0 * m * m * (gsm_ is not None) + 8.0 * r * m * (x is not None) + 40.0 + 4.0
+    nbytes = lib.mf_sweep_f64_ws_bytes(r, m, nf, variant)
+    ws = workspaces.get("sweep", nbytes, dev)
     with _timed("sweep_lu_gsm", nbytes=bytes_pt * nf, flops=flops_pt * nf):
         _ffi.check(lib.mf_sweep_lu_gsm_f64(_ptr(a0s), _ptr(a1s), _ptr(a2s), lda, _ptr(br), br.stride(0), r, m,
-                                           _ptr(c0), _ptr(c1), _ptr(c2), _ptr(cb), _ptr(zscale), nf, _ptr(x), _ptr(gsm_), _ptr(info), _stream()),
+                                           _ptr(c0), _ptr(c1), _ptr(c2), _ptr(cb), _ptr(zscale), nf, _ptr(x), _ptr(gsm_), _ptr(info),
+                                           variant, _ptr(ws), ws.numel(), _stream()),
                    "mf_sweep_lu_gsm_f64")
     return SweepResult(x, gsm_, info)
 

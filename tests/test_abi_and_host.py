@@ -57,16 +57,20 @@ def test_argument_validation_without_gpu():
     assert lib.mf_spmm_csr_f64(None, None, None, 10, None, 4, 4, None, 4, None) == -1
     assert lib.mf_spmm_group_count(None, None, 10, 4, None, None) == -1
     assert lib.mf_spmm_grouped_c128(None, None, None, 10, 4, None, 4, 4, None, 4, None) == -1
-    assert lib.mf_sweep_lu_gsm_f64(None, None, None, 8, None, 2, 8, 2, None, None, None, None, None, 4, None, None, None, None) == -1
+    assert lib.mf_sweep_lu_gsm_f64(None, None, None, 8, None, 2, 8, 2, None, None, None, None, None, 4, None, None, None, 0, None, 0, None) == -1
     assert lib.mf_jacobi_svd_f64(None, 4, 4, None, 4, None, 10, 1e-15, None, None) == -1
     assert lib.mf_gemm_tn_f64_ws_bytes(64, 64, 100000) >= 64 * 64 * 8
     # shape support queries (host only): which kernel family serves which (r, m)
     assert lib.mf_spmm_group_size(64) == 4 and lib.mf_spmm_group_size(256) == 2
-    assert lib.mf_sweep_f64_supported(64, 2) == 1 and lib.mf_sweep_f64_supported(256, 4) == 0
+    assert lib.mf_sweep_f64_supported(64, 2) == 1 and lib.mf_sweep_f64_supported(256, 4) == 1 and lib.mf_sweep_f64_supported(513, 4) == 0
+    assert lib.mf_sweep_f64_variant_supported(256, 4, 3) == 0 and lib.mf_sweep_f64_variant_supported(256, 4, 5) == 1
+    assert lib.mf_sweep_f64_ws_bytes(64, 2, 1000, 0) == 256 and lib.mf_sweep_f64_ws_bytes(256, 4, 1000, 0) >= 148 * 2 * 256 * 256 * 8
+    assert lib.mf_sweep_variant_supported(256, 4, 4) == 1 and lib.mf_sweep_variant_supported(64, 2, 4) == 0 and lib.mf_sweep_variant_supported(64, 2, 5) == 1
     assert lib.mf_jacobi_svd_f64_supported(64) == 1 and lib.mf_jacobi_svd_f64_supported(65) == 0
     assert all(lib.mf_sweep_variant_supported(r, 4, 3) == 1 for r in (1, 64, 112, 113, 256, 512))
     assert lib.mf_sweep_variant_supported(600, 4, 3) == 0 and lib.mf_sweep_variant_supported(600, 4, 1) == 1
-    assert lib.mf_sweep_ws_bytes(256, 4, 1000, 0) >= 148 * 256 * 264 * 16 and lib.mf_sweep_ws_bytes(64, 2, 1000, 0) == 256
+    assert lib.mf_sweep_ws_bytes(256, 4, 1000, 0) >= 148 * 2 * 256 * 256 * 16 and lib.mf_sweep_ws_bytes(64, 2, 1000, 0) == 256
+    assert lib.mf_sweep_ws_bytes(256, 4, 1000, 4) >= 148 * 256 * 264 * 16
 
 
 def test_product_path_refuses_to_run_without_cuda():
@@ -154,11 +158,26 @@ def test_streamed_sweep_geometry_from_workspace_sizes(monkeypatch):
     slot = lambda r, m: 16 * ((r + 31) // 32 * 32) * ((r + 31) // 32 * 32 + (m + 7) // 8 * 8)
     big = 10 ** 6
     per_sm = {(113, 1): 3, (128, 4): 3, (129, 4): 2, (256, 4): 2, (257, 4): 1, (512, 8): 1}
-    sms = lib.mf_sweep_ws_bytes(512, 8, big, 3) // slot(512, 8)
+    sms = lib.mf_sweep_ws_bytes(512, 8, big, 4) // slot(512, 8)
     assert sms >= 1
     for (r, m), ctas in per_sm.items():
-        assert lib.mf_sweep_ws_bytes(r, m, big, 3) == ctas * sms * slot(r, m), (r, m)
-        assert lib.mf_sweep_ws_bytes(r, m, 10, 3) == 10 * slot(r, m)          # never more slots than points
+        assert lib.mf_sweep_ws_bytes(r, m, big, 4) == ctas * sms * slot(r, m), (r, m)
+        assert lib.mf_sweep_ws_bytes(r, m, 10, 4) == 10 * slot(r, m)          # never more slots than points
     monkeypatch.setenv("MF_STREAM_CFG", "0")
-    assert lib.mf_sweep_ws_bytes(256, 4, big, 3) == sms * slot(256, 4)
+    assert lib.mf_sweep_ws_bytes(256, 4, big, 4) == sms * slot(256, 4)
     assert lib.mf_sweep_ws_bytes(64, 2, big, 3) <= 256                         # r <= 112: matrix lives in shared memory
+
+
+def test_left_looking_sweep_workspace_sizes():
+    """The left-looking sweep (variant 5; what variant 3 runs above r = 112) keeps, per resident CTA, the multiplier panels
+    (R x R, indexed by original row), the U blocks (R x R, fragment order) and the inverted 16 x 16 diagonal blocks of L and U
+    (2 x 16 R), R = r rounded up to 16; float64 slots are half the size of complex128 ones."""
+    from morfem_b200 import _ffi
+    lib = _ffi.load()
+    slot = lambda r: ((r + 15) // 16 * 16) ** 2 * 2 + 32 * ((r + 15) // 16 * 16)
+    for r, m in ((113, 1), (160, 4), (256, 4), (300, 2), (512, 8)):
+        assert lib.mf_sweep_ws_bytes(r, m, 10, 5) == 10 * 16 * slot(r)
+        assert lib.mf_sweep_ws_bytes(r, m, 10, 3) == 10 * 16 * slot(r)
+        assert lib.mf_sweep_f64_ws_bytes(r, m, 10, 0) == (10 * 8 * slot(r) if r > 128 else 256)     # float64: shared memory holds r <= 128
+        assert lib.mf_sweep_f64_ws_bytes(r, m, 10, 5) == 10 * 8 * slot(r)
+    assert lib.mf_sweep_ws_bytes(64, 2, 10, 5) == 10 * 16 * slot(64) and lib.mf_sweep_f64_ws_bytes(64, 2, 10, 5) == 10 * 8 * slot(64)

@@ -47,7 +47,7 @@ def per_point_rel(new, ref):
 def variants_for(dv, r, m):
     from morfem_b200 import _ffi
     lib = _ffi.load()
-    return [v for v in (1, 2, 3) if lib.mf_sweep_variant_supported(r, m, v)]
+    return [v for v in (1, 2, 3, 4, 5) if lib.mf_sweep_variant_supported(r, m, v)]
 
 
 @pytest.mark.parametrize("name", REDUCED)
@@ -194,14 +194,21 @@ def test_sweep_large_batch_property(dv):
 
 
 # ---------------------------------------------------------------------------------- real float64 twin (row N2)
-def run_sweep_real(dv, f, a0, a1, a2, b, cb, want_x=True, want_gsm=True):
+def run_sweep_real(dv, f, a0, a1, a2, b, cb, want_x=True, want_gsm=True, variant=0):
     from scipy.constants import pi, epsilon_0
     dev = dv.require_cuda()
     t = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(dev)  # noqa: E731
     ops = [None if (a is None or not np.any(a)) else dv.symmetrize(t(a)) for a in (a0, a1, a2)]
-    res = dv.sweep(ops[0], ops[1], ops[2], t(b), t(np.ones_like(f)), t(f), t(f ** 2), t(cb), t(2 * pi * f * epsilon_0), want_x=want_x, want_gsm=want_gsm)
+    res = dv.sweep(ops[0], ops[1], ops[2], t(b), t(np.ones_like(f)), t(f), t(f ** 2), t(cb), t(2 * pi * f * epsilon_0), want_x=want_x, want_gsm=want_gsm,
+                   variant=variant)
     torch.cuda.synchronize()
     return res
+
+
+def real_variants_for(r, m):
+    from morfem_b200 import _ffi
+    lib = _ffi.load()
+    return [v for v in (3, 5) if lib.mf_sweep_f64_variant_supported(r, m, v)]
 
 
 @pytest.mark.parametrize("name", REDUCED)
@@ -209,32 +216,56 @@ def test_real_sweep_matches_live_reference_fixture(dv, name):
     g = np.load(os.path.join(GOLDEN, name + ".npz"))
     f = g["f"]
     cb = np.array([orc.b_coefficient(t) for t in f])
-    res = run_sweep_real(dv, f, g["a0"], g["a1"], g["a2"], g["b"], cb)
     r, m = g["b"].shape
-    from morfem_b200 import _ffi
-    expect_real = bool(_ffi.load().mf_sweep_f64_supported(r, m))
-    assert (res.x.dtype == torch.float64) == expect_real          # larger models fall back to the complex128 kernels
-    x = res.x.cpu().numpy()
     tol = np.maximum(1e-10, 20 * EPS * g["cond"])
-    assert not np.any(res.info.cpu().numpy())
-    assert np.all(per_point_rel(x.real, g["x"]) < tol) and np.all(per_point_rel(res.gsm.cpu().numpy(), g["gsm"]) < tol)
+    for variant in [0] + real_variants_for(r, m):
+        res = run_sweep_real(dv, f, g["a0"], g["a1"], g["a2"], g["b"], cb, variant=variant)
+        assert res.x.dtype == torch.float64                        # every size up to r = 512 has a real kernel (the reference's dtype)
+        x = res.x.cpu().numpy()
+        assert not np.any(res.info.cpu().numpy())
+        assert np.all(per_point_rel(x, g["x"]) < tol) and np.all(per_point_rel(res.gsm.cpu().numpy(), g["gsm"]) < tol), variant
 
 
-@pytest.mark.parametrize("r,m,nf", [(1, 1, 3), (7, 3, 33), (16, 16, 9), (31, 5, 40), (64, 2, 500), (100, 8, 12), (128, 4, 6)])
+@pytest.mark.parametrize("r,m,nf", [(1, 1, 3), (7, 3, 33), (16, 16, 9), (31, 5, 40), (64, 2, 500), (100, 8, 12), (128, 4, 6),
+                                    (129, 1, 5), (160, 4, 300), (200, 9, 7), (256, 4, 40), (300, 2, 3), (512, 8, 150)])
 def test_real_sweep_equals_complex_sweep_and_oracle(dv, r, m, nf):
     from morfem_b200 import synthetic
     a0, a1, a2, b = synthetic.reduced_model(r, m, seed=100 + r)
     f = np.linspace(3e9, 5e9, nf)
     tb = orc.b_coefficient
     cb = np.array([tb(t) for t in f])
-    real = run_sweep_real(dv, f, a0, a1, a2, b, cb)
-    cplx = run_sweep(dv, f, a0, a1, a2, b, cb, variant=3)
-    assert real.x.dtype == torch.float64
-    assert np.all(per_point_rel(real.x.cpu().numpy(), cplx.x.cpu().numpy().real) < 1e-12)       # same algorithm, same pivots
-    assert np.all(per_point_rel(real.gsm.cpu().numpy(), cplx.gsm.cpu().numpy()) < 1e-12)
     x_ref = orc.reduced_sweep(f, a0, a1, a2, b, lambda t: 1.0, lambda t: t, lambda t: t ** 2, tb)
+    s_ref = orc.scattering_sweep(f, x_ref, b)
     cond = np.array([np.linalg.cond(orc.system_matrix(1.0, t, t ** 2, a0, a1, a2)) for t in f])
-    assert np.all(per_point_rel(real.x.cpu().numpy(), x_ref) < np.maximum(1e-10, 20 * EPS * cond))
+    tol = np.maximum(1e-10, 20 * EPS * cond)
+    for variant in real_variants_for(r, m):
+        real = run_sweep_real(dv, f, a0, a1, a2, b, cb, variant=variant)
+        cplx = run_sweep(dv, f, a0, a1, a2, b, cb, variant=variant)          # the complex128 instance of the same kernel
+        assert real.x.dtype == torch.float64
+        assert not np.any(real.info.cpu().numpy())
+        assert np.all(per_point_rel(real.x.cpu().numpy(), cplx.x.cpu().numpy().real) < 1e-12), variant    # same algorithm, same pivots
+        assert np.all(per_point_rel(real.gsm.cpu().numpy(), cplx.gsm.cpu().numpy()) < 1e-12), variant
+        assert np.all(per_point_rel(real.x.cpu().numpy(), x_ref) < tol), variant
+        assert np.all(per_point_rel(real.gsm.cpu().numpy(), s_ref) < tol), variant
+
+
+def test_real_left_looking_sweep_pivots_and_reports_singular_points(dv):
+    """The float64 left-looking kernel on a permutation-like matrix (an exchange in every column of every panel) and on an
+    exactly singular one (first zero pivot deep inside the fifth panel)."""
+    r, m = 150, 2
+    rng = np.random.default_rng(8)
+    a0 = np.fliplr(np.eye(r)) * 2.0 + 1e-3 * rng.standard_normal((r, r))
+    a0 = (a0 + a0.T) / 2
+    b = rng.standard_normal((r, m))
+    f = np.array([3e9, 4e9, 5e9])
+    zero = np.zeros((r, r))
+    x_ref = orc.reduced_sweep(f, a0, zero, zero, b, lambda t: 1.0, lambda t: t, lambda t: t ** 2, lambda t: 1.0)
+    res = run_sweep_real(dv, f, a0, None, None, b, np.ones(3), variant=5)
+    assert np.all(per_point_rel(res.x.cpu().numpy(), x_ref) < 1e-11)
+    sing = np.eye(r)
+    sing[77, 77] = 0.0
+    res = run_sweep_real(dv, f, sing, None, None, np.ones((r, m)), np.ones(3), variant=5, want_gsm=False)
+    assert list(res.info.cpu().numpy()) == [78, 78, 78]
 
 
 def test_real_sweep_reports_singular_points(dv):
