@@ -112,6 +112,21 @@ int mf_spmm_group_fill(const int32_t* rowptr, const int32_t* colidx, const doubl
 int mf_spmm_grouped_c128(const int64_t* ustart, const int32_t* ucols, const double* uvals, int64_t nrows, int G,
                          const mf_c128* Q, int64_t ldq, int r, mf_c128* Y, int64_t ldy, void* stream);
 
+/* Windowed SpMM with TMA staging (the north star's "Q tiles staged in shared memory by TMA"), same product as mf_spmm_csr_*
+ * for REAL operator values.  One CTA per block of mf_spmm_window_rows_per_block() consecutive rows; the distinct Q rows the
+ * block references (its window: ucol[wstart[b] .. wstart[b+1]), at most wmax <= mf_spmm_window_max_rows() of them) are fetched
+ * slice by slice with bulk asynchronous copies (cp.async.bulk + mbarrier) and reused from shared memory by all rows of the
+ * block; slot[k] is the position of non-zero k's column inside its block's window (8 bits instead of a 32-bit column index).
+ * Rows may hold at most mf_spmm_window_max_nnz_per_row() non-zeros.  The window lists are built once per operator on the host
+ * (morfem_b200.device.build_windows).  Kept as the measured alternative to the row-grouped kernel (profiles/r02_spmm.md). */
+int mf_spmm_window_rows_per_block(void);
+int mf_spmm_window_max_nnz_per_row(void);
+int mf_spmm_window_max_rows(void);
+int mf_spmm_window_c128(const int32_t* rowptr, const uint8_t* slot, const double* vals, const int32_t* wstart, const int32_t* ucol,
+                        int64_t nrows, int wmax, const mf_c128* Q, int64_t ldq, int r, mf_c128* Y, int64_t ldy, void* stream);
+int mf_spmm_window_f64(const int32_t* rowptr, const uint8_t* slot, const double* vals, const int32_t* wstart, const int32_t* ucol,
+                       int64_t nrows, int wmax, const double* Q, int64_t ldq, int r, double* Y, int64_t ldy, void* stream);
+
 /* B_r (r x m) = Q^T B (conj_q != 0: Q^H B) for B in CSC (n x m, int32 indices, real or complex values);
  * implementation.py:184 `q_t @ md.b`.  Rows outside [row0, row0 + nlocal) are skipped so that row-sharded
  * callers can all-reduce the partial results; Q points at the caller's first local row. */

@@ -49,6 +49,13 @@ SIGNATURES = {
     "mf_spmm_group_fill": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "mf_spmm_grouped_c128": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_int64, c_int, c_void_p, c_int64,
                                      c_void_p]),
+    "mf_spmm_window_rows_per_block": (c_int, []),
+    "mf_spmm_window_max_nnz_per_row": (c_int, []),
+    "mf_spmm_window_max_rows": (c_int, []),
+    "mf_spmm_window_c128": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_int64, c_int, c_void_p, c_int64,
+                                    c_void_p]),
+    "mf_spmm_window_f64": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_int64, c_int, c_void_p, c_int64,
+                                   c_void_p]),
     "mf_project_rhs_c128": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int64, c_int, c_int64, c_int64,
                                     c_int, c_void_p, c_int64, c_void_p]),
     "mf_gemm_tn_f64_ws_bytes": (c_size_t, [c_int, c_int, c_int64]),

@@ -7,6 +7,7 @@
 // critical path; for every non-zero the warp streams the whole Q row (r * 16 B, contiguous) with 128-bit loads,
 // CPL independent loads per lane in flight, and accumulates in registers.  Y rows are written once, coalesced.
 // HBM-bound: algorithmic bytes nnz*(idx+val) + 4(N+1) + 2*N*r*16.
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace {
@@ -220,6 +221,8 @@ spmm_grouped_kernel(const long long* __restrict__ ustart, const int* __restrict_
                     const cplx* __restrict__ Q, long long ldq, int r, cplx* __restrict__ Y, long long ldy) {
     const long long g = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
+    // blockIdx.y selects a slice of 32 CPL columns (wide bases: more rows per group fit the accumulator registers)
+    Q += (long long)blockIdx.y * 32 * CPL; Y += (long long)blockIdx.y * 32 * CPL; r -= (int)blockIdx.y * 32 * CPL;
     __shared__ __align__(16) double cstage[8][32 * G];
     double* cw = cstage[(threadIdx.x >> 5) & 7];
     if (g * G >= nrows) return;
@@ -337,6 +340,7 @@ spmm_grouped_f64_kernel(const long long* __restrict__ ustart, const int* __restr
                         const double* __restrict__ Q, long long ldq, int r, double* __restrict__ Y, long long ldy) {
     const long long g = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
+    Q += (long long)blockIdx.y * 32 * CPL; Y += (long long)blockIdx.y * 32 * CPL; r -= (int)blockIdx.y * 32 * CPL;    // column slice
     __shared__ __align__(16) double cstage[8][32 * G];
     double* cw = cstage[(threadIdx.x >> 5) & 7];
     if (g * G >= nrows) return;
@@ -445,7 +449,15 @@ extern "C" int mf_project_rhs_c128(const int32_t* colptr, const int32_t* rowidx,
     return 0;
 }
 
-extern "C" int mf_spmm_group_size(int r) { return r <= 128 ? 4 : 2; }
+// Rows per group.  Four rows share one column-union list (a Q row is pulled through L1 once for four output rows); above
+// r = 128 the accumulators of four full rows no longer fit the register file, so the complex kernel runs column slices of
+// 128 (blockIdx.y) instead of falling back to two rows per group.  MF_SPMM_SPLIT=0 restores the round-1 policy (2 rows, full width).
+static bool spmm_split_mode() {
+    static int mode = -1;
+    if (mode < 0) { const char* e = getenv("MF_SPMM_SPLIT"); mode = (e && atoi(e) == 0) ? 0 : 1; }
+    return mode == 1;
+}
+extern "C" int mf_spmm_group_size(int r) { return (r <= 128 || spmm_split_mode()) ? 4 : 2; }
 
 extern "C" int mf_spmm_group_count(const int32_t* rowptr, const int32_t* colidx, int64_t nrows, int G, int32_t* counts, void* stream) {
     if (!rowptr) MF_FAIL_ARG(1, "rowptr is NULL");
@@ -496,12 +508,13 @@ extern "C" int mf_spmm_grouped_c128(const int64_t* ustart, const int32_t* ucols,
     const long long ngroups = (nrows + G - 1) / G;
     const long long blocks = (ngroups * 32 + 255) / 256;
     if (blocks > 0x7fffffffLL) MF_FAIL_ARG(4, "nrows too large for one launch");
-#define GSPMM(GG, C) spmm_grouped_kernel<GG, C><<<(unsigned)blocks, 256, 0, st>>>((const long long*)ustart, ucols, uvals, nrows, (const cplx*)Q, ldq, r, (cplx*)Y, ldy)
-    if (r <= 32) GSPMM(4, 1);
-    else if (r <= 64) GSPMM(4, 2);
-    else if (r <= 128) GSPMM(4, 4);
-    else if (r <= 256) GSPMM(2, 8);
-    else GSPMM(2, 16);
+#define GSPMM(GG, C, NY) spmm_grouped_kernel<GG, C><<<dim3((unsigned)blocks, NY), 256, 0, st>>>((const long long*)ustart, ucols, uvals, nrows, (const cplx*)Q, ldq, r, (cplx*)Y, ldy)
+    if (r <= 32) GSPMM(4, 1, 1);
+    else if (r <= 64) GSPMM(4, 2, 1);
+    else if (r <= 128) GSPMM(4, 4, 1);
+    else if (G == 4) GSPMM(4, 4, (r + 127) / 128);                 // column slices of 128
+    else if (r <= 256) GSPMM(2, 8, 1);
+    else GSPMM(2, 16, 1);
 #undef GSPMM
     MF_CHECK_LAUNCH();
     return 0;
@@ -542,8 +555,10 @@ extern "C" int mf_spmm_grouped_f64(const int64_t* ustart, const int32_t* ucols, 
     const long long ngroups = (nrows + G - 1) / G;
     const long long blocks = (ngroups * 32 + 255) / 256;
     if (blocks > 0x7fffffffLL) MF_FAIL_ARG(4, "nrows too large for one launch");
-#define GRSPMM(GG, C) spmm_grouped_f64_kernel<GG, C><<<(unsigned)blocks, 256, 0, st>>>((const long long*)ustart, ucols, uvals, nrows, Q, ldq, r, Y, ldy)
-    if (r <= 32) GRSPMM(4, 1); else if (r <= 64) GRSPMM(4, 2); else if (r <= 128) GRSPMM(4, 4); else if (r <= 256) GRSPMM(2, 8); else GRSPMM(2, 16);
+#define GRSPMM(GG, C, NY) spmm_grouped_f64_kernel<GG, C><<<dim3((unsigned)blocks, NY), 256, 0, st>>>((const long long*)ustart, ucols, uvals, nrows, Q, ldq, r, Y, ldy)
+    if (r <= 32) GRSPMM(4, 1, 1); else if (r <= 64) GRSPMM(4, 2, 1); else if (r <= 128) GRSPMM(4, 4, 1);
+    else if (G == 4) GRSPMM(4, 8, (r + 255) / 256);                // float64: four rows of 256 columns fit; slices of 256 above
+    else if (r <= 256) GRSPMM(2, 8, 1); else GRSPMM(2, 16, 1);
 #undef GRSPMM
     MF_CHECK_LAUNCH();
     return 0;

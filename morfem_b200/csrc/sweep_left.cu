@@ -126,6 +126,13 @@ __device__ __forceinline__ void panel_factor_t(T* PB, const int LDp, const int r
                                                CandKeyL* candk, T* candrow, int* pvl, int* info_sh, const int info_base) {
     constexpr int NT = NW * 32;
     const int lane = tid & 31, warp = tid >> 5;
+    // warps whose first row lies beyond the panel take part in the eight column barriers only
+    const int nact = min(NW, (rows - row0 + 31) >> 5);
+    if (warp >= nact) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) __syncthreads();
+        return;
+    }
     T a[SL][8];
     int pos[SL];
     bool act[SL];
@@ -178,7 +185,7 @@ __device__ __forceinline__ void panel_factor_t(T* PB, const int LDp, const int r
         __syncthreads();
         // global winner among the NW warp candidates: lane w looks at candidate w, then the same warp arg-max
         double cv = -2.0; int cp = 0x7fffffff;
-        if (lane < NW) {
+        if (lane < nact) {
             const unsigned cks = (unsigned)__cvta_generic_to_shared(ck + lane);
             long long pbits;
             asm volatile("ld.volatile.shared.v2.b64 {%0, %1}, [%2];" : "=d"(cv), "=l"(pbits) : "r"(cks));
@@ -608,6 +615,428 @@ __global__ void __launch_bounds__(NW * 32, MINB) sweep_left_kernel(SweepParamsL<
 }
 
 
+// ======================================================================================================================
+// Version 2 of the kernel body.  Same algorithm and storage as above, restructured after the first ncu capture
+// (profiles/r02_sweep_left_v1_ncu.md: 1.23 M warp instructions per point of which 8 % DMMA; 24 % of the stall samples at the
+// per-step CTA barrier of the chain):
+//   * accumulators live in the register form DMMA wants (re[2] / im[2] quads) -- no register shuffles around the MMAs;
+//   * ownership by 8-row TILE, cyclic over the warps, and a static (unrolled) unit loop with a closed-form prefetch
+//     iterator instead of the dynamic one;
+//   * the chain is dataflow: U[k, j] is announced by one flag word per tile, consumers wait on the two flags they need,
+//     there is no CTA barrier inside a block column's chain;
+//   * the rows of a finished 16-row block are multiplied by the inverse of their unit-lower diagonal block ONCE, when the
+//     block is factored ("L~[b, k] = L_bb^-1 (-L[b, k])", in place in global memory); a later block column then gets
+//     U[b, j] = L_bb^-1 A[b, j] + sum_k L~[b, k] U[k, j] with the first product at load time, so a chain link is ONE
+//     8 x 16 x 16 tile update plus the publication -- no triangular product on the critical path;
+//   * operator loads are branch-free (all in flight at once); warps without rows skip the panel arithmetic.
+// ======================================================================================================================
+template <typename T> struct Acc;
+template <> struct Acc<double> {                                  // one 8 x 8 tile: lane (g, t) holds row g, columns 2t, 2t + 1
+    double v[2];
+    __device__ __forceinline__ void zero() { v[0] = 0.0; v[1] = 0.0; }
+    __device__ __forceinline__ void mma1(double a, double b) { dmma884(v[0], v[1], a, b); }
+    __device__ __forceinline__ void mma2(double, double) {}
+    __device__ __forceinline__ double get(int e) const { return v[e]; }
+    __device__ __forceinline__ void set(int e, double x) { v[e] = x; }
+};
+template <> struct Acc<cplx> {
+    double re[2], im[2];
+    __device__ __forceinline__ void zero() { re[0] = re[1] = im[0] = im[1] = 0.0; }
+    // the four real DMMAs of a complex block product, issued as two passes so that DMMAs on one accumulator are far apart
+    __device__ __forceinline__ void mma1(cplx a, cplx b) { dmma884(re[0], re[1], a.x, b.x); dmma884(im[0], im[1], a.x, b.y); }
+    __device__ __forceinline__ void mma2(cplx a, cplx b) { dmma884(re[0], re[1], -a.y, b.y); dmma884(im[0], im[1], a.y, b.x); }
+    __device__ __forceinline__ cplx get(int e) const { return cmake(re[e], im[e]); }
+    __device__ __forceinline__ void set(int e, cplx x) { re[e] = x.x; im[e] = x.y; }
+};
+
+// NW warps; warp w owns the 8-row tiles w, w + NW, ... (TPW of them at most); MINB CTAs per SM; NSTAGE = FIFO depth.
+template <typename T, int NW, int TPW, int MINB, int NSTAGE>
+__global__ void __launch_bounds__(NW * 32, MINB) sweep_left2_kernel(SweepParamsL<T> p, int R) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int NT = NW * 32;
+    constexpr int SL = (TPW + 3) / 4;                            // rows per thread in the panel factorisation (R <= 8 NW TPW)
+    constexpr int RBW = (TPW + 1) / 2;                           // 16-row blocks per warp in the back substitution
+    const int r = p.r, m = p.m, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, tl = lane & 3;
+    const int nb = R >> 4, ntiles = R >> 3;
+    const int mct = (m + 7) >> 3;
+
+    T* BC = reinterpret_cast<T*>(smem_raw);                      // R x 16: U blocks (fragment order) | panel rows (swizzled)
+    T* ring = BC + (size_t)R * 16;                               // NW x NSTAGE x 128: per-lane FIFO of L fragments
+    T* xch = ring + (size_t)NW * NSTAGE * 128;                   // 256: inverse of the current unit-lower block (A order) / exchange
+    T* candrow = xch + 256;                                      // 2 x NW x 8
+    CandKeyL* candk = reinterpret_cast<CandKeyL*>(candrow + 2 * NW * 8);   // 2 x NW
+    int* perm = reinterpret_cast<int*>(candk + 2 * NW);          // R: position -> original row
+    int* uflag = perm + R;                                       // R / 8: epoch at which tile t of the current block column was published
+    int* lp = uflag + (R >> 3);                                  // 16 local pivot positions of the current panel
+    int* info_sh = lp + 16;
+
+    T* Lg = p.ws + (long long)blockIdx.x * p.ws_stride;          // [nb][R original rows][16]: negated multipliers (L~ for finished blocks)
+    T* Ug = Lg + (long long)nb * R * 16;                         // [nb][nb][256]: U[b, k] in A-fragment order
+    T* LIg = Ug + (long long)nb * nb * 256;                      // [nb][256]: inverse of the unit-lower diagonal blocks (A order)
+    T* UIg = LIg + (long long)nb * 256;                          // [nb][256]: inverse of the upper diagonal blocks (A order)
+    T* ringw = ring + (size_t)warp * NSTAGE * 128;
+    const bool hasA0 = p.A0 != nullptr, hasA1 = p.A1 != nullptr, hasA2 = p.A2 != nullptr;
+    const int imax = min(TPW, max(0, (ntiles - warp + NW - 1) / NW));        // owned tiles: t = warp + NW i, i < imax
+
+    FragOff fop;
+    {
+        const int sg = swz(g);
+        fop.g = g; fop.a0 = tl ^ sg; fop.a1 = (4 + tl) ^ sg; fop.c0 = (2 * tl) ^ sg; fop.c1 = (2 * tl + 1) ^ sg;
+        fop.b0 = tl * 16 + (g ^ swz(tl)); fop.b1 = (4 + tl) * 16 + (g ^ swz(4 + tl));
+    }
+    for (int i = tid; i < (R >> 3); i += NT) uflag[i] = 0;
+    int epoch = 0;
+
+    for (long long pt = blockIdx.x; pt < p.F; pt += gridDim.x) {
+        const double c0 = p.c0[pt], c1 = p.c1[pt], c2 = p.c2[pt], cb = p.cb[pt];
+        for (int i = tid; i < R; i += NT) perm[i] = i;
+        if (tid == 0) *info_sh = 0;
+        __syncthreads();
+
+        Acc<T> C[TPW][2];                                        // [owned tile][column tile]
+
+        for (int j = 0; j <= nb; ++j) {
+            const bool isrhs = (j == nb);
+            const int jj = isrhs ? nb : j;
+            const int nct = isrhs ? mct : 2;
+            ++epoch;
+
+            // element (original row o, local column cl) of block column j of [A(t) | cb Br]; branch-free so that all loads of a
+            // tile are in flight together (identity on the padded diagonal)
+            auto elem = [&](const int o, const int cl) -> T {
+                if (isrhs) {
+                    const bool in = (o < r) & (cl < m);
+                    const T x = __ldg(p.Br + (in ? (long long)o * p.ldb + cl : 0));
+                    return in ? Num<T>::scale(cb, x) : Num<T>::zero();
+                }
+                const int cg = 16 * j + cl;
+                const bool in = (o < r) & (cg < r);
+                const long long off = in ? (long long)o * p.lda + cg : 0;
+                T v = Num<T>::zero();
+                if (hasA0) v = Num<T>::scale(c0, __ldg(p.A0 + off));
+                if (hasA1) Num<T>::axpy(v, c1, __ldg(p.A1 + off));
+                if (hasA2) Num<T>::axpy(v, c2, __ldg(p.A2 + off));
+                return in ? v : ((o == cg) ? Num<T>::one() : Num<T>::zero());
+            };
+
+            // ---- LOAD ----
+            int obase[TPW];                                      // per owned tile: 16 * (original row of lane's row) + tl
+#pragma unroll
+            for (int i = 0; i < TPW; ++i) {
+                const int t = warp + NW * i;
+                obase[i] = 0;
+                C[i][0].zero(); C[i][1].zero();
+                if (i < imax) {
+                    const int o = perm[8 * t + g];
+                    obase[i] = o * 16 + tl;
+                    if (t >= 2 * jj) {                           // rows at or below the diagonal block: the plain matrix elements
+#pragma unroll
+                        for (int ct = 0; ct < 2; ++ct)
+#pragma unroll
+                            for (int e = 0; e < 2; ++e) C[i][ct].set(e, elem(o, 8 * ct + 2 * tl + e));
+                    } else {                                     // rows of a finished block b: L_bb^-1 A[b, j] (lower triangular inverse)
+                        const int b = t >> 1, h = t & 1;
+                        const T* li = LIg + (long long)b * 256 + ((h * 4) << 5) + lane;
+#pragma unroll
+                        for (int kk = 0; kk < 4; ++kk) {
+                            if (kk < 2 || h == 1) {
+                                const T a = li[kk << 5];
+                                const int ok = perm[16 * b + 4 * kk + tl];
+                                const T b0 = elem(ok, g), b1 = elem(ok, 8 + g);
+                                C[i][0].mma1(a, b0); if (nct > 1) C[i][1].mma1(a, b1);
+                                C[i][0].mma2(a, b0); if (nct > 1) C[i][1].mma2(a, b1);
+                            }
+                        }
+                    }
+                }
+            }
+
+            // U rows of a finished tile -> shared slot (B-fragment order), global (A-fragment order, for the back substitution), flag
+            auto publish = [&](const Acc<T> (&Ct)[2], const int t) {
+                const int b = t >> 1, h = t & 1;
+                T* slot = BC + b * 256;
+#pragma unroll
+                for (int ct = 0; ct < 2; ++ct)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) slot[bfrag_off(8 * h + g, 8 * ct + 2 * tl + e)] = Ct[ct].get(e);
+                if (!isrhs) {
+                    T* ub = Ug + ((long long)b * nb + j) * 256;
+#pragma unroll
+                    for (int ct = 0; ct < 2; ++ct) {
+                        T* dst = ub + afrag_off(8 * h + g, 8 * ct + 2 * tl);
+                        dst[0] = Ct[ct].get(0); dst[1] = Ct[ct].get(1);
+                    }
+                }
+                __syncwarp();
+                __threadfence_block();
+                if (lane == 0) *reinterpret_cast<volatile int*>(uflag + t) = epoch;
+            };
+
+            // ---- CHAIN ----
+            if (jj > 0) {
+                // units of this warp: (step k, owned tile i) with t = warp + NW i >= 2 (k + 1); i runs from i0(k) to imax - 1
+                auto i0 = [&](const int k) { const int d = 2 * (k + 1) - warp; return d <= 0 ? 0 : (d + NW - 1) / NW; };
+                int pk = 0, pi = i0(0);
+                auto pnorm = [&]() { while (pk < jj && pi >= imax) { ++pk; pi = i0(pk); } };
+                auto issue = [&](const int stage) {
+                    int ob = obase[0];
+#pragma unroll
+                    for (int i = 1; i < TPW; ++i) ob = (pi == i) ? obase[i] : ob;
+                    const T* src = Lg + (long long)pk * R * 16 + ob;
+                    T* dst = ringw + stage * 128 + lane;
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk) Num<T>::cp_async(dst + 32 * kk, src + 4 * kk);
+                };
+                pnorm();
+                int pstage = 0, cstage = 0;
+#pragma unroll
+                for (int st = 0; st < NSTAGE - 1; ++st) {
+                    if (pk < jj) { issue(pstage); ++pi; pnorm(); }
+                    cpa_commit();
+                    pstage = (pstage + 1 == NSTAGE) ? 0 : pstage + 1;
+                }
+#pragma unroll
+                for (int i = 0; i < TPW; ++i)                    // block 0 needs no update: U[0, j] = L_00^-1 A[0, j] is final
+                    if (i < imax && warp + NW * i < 2) publish(C[i], warp + NW * i);
+#pragma unroll 1
+                for (int k = 0; k < jj; ++k) {
+                    const int ifirst = i0(k);
+                    if (ifirst >= imax) continue;                // no tile of this warp below block k any more
+                    {                                            // wait for both halves of U[k, j]
+                        volatile int* f = uflag + 2 * k;
+                        while (f[0] != epoch || f[1] != epoch) { }
+                        __threadfence_block();
+                    }
+                    const T* Uk = BC + k * 256 + lane;
+#pragma unroll
+                    for (int i = 0; i < TPW; ++i) {
+                        if (i >= ifirst && i < imax) {
+                            if (pk < jj) { issue(pstage); ++pi; pnorm(); }
+                            cpa_commit();
+                            pstage = (pstage + 1 == NSTAGE) ? 0 : pstage + 1;
+                            cpa_wait<NSTAGE - 1>();
+                            const T* af = ringw + cstage * 128 + lane;
+                            cstage = (cstage + 1 == NSTAGE) ? 0 : cstage + 1;
+#pragma unroll
+                            for (int kk = 0; kk < 4; ++kk) {
+                                const T a = af[32 * kk];
+                                const T b0 = Uk[(kk * 2) << 5], b1 = Uk[(kk * 2 + 1) << 5];
+                                C[i][0].mma1(a, b0); if (nct > 1) C[i][1].mma1(a, b1);
+                                C[i][0].mma2(a, b0); if (nct > 1) C[i][1].mma2(a, b1);
+                            }
+                            const int t = warp + NW * i;
+                            if ((t >> 1) == k + 1 && k + 1 < jj) publish(C[i], t);      // the tile's last update: its U rows are final
+                        }
+                    }
+                }
+                cpa_wait<0>();
+            }
+            if (isrhs) break;
+
+            // ---- PANEL: rows at positions >= 16 j -> shared memory (swizzled), LU with partial pivoting ----
+            T* PB = BC + (size_t)j * 256;
+            const int rows = R - 16 * j;
+#pragma unroll
+            for (int i = 0; i < TPW; ++i) {
+                const int t = warp + NW * i;
+                if (i < imax && t >= 2 * j) {
+#pragma unroll
+                    for (int ct = 0; ct < 2; ++ct)
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) PB[mphys(8 * (t - 2 * j) + g, 8 * ct + 2 * tl + e, 16)] = C[i][ct].get(e);
+                }
+            }
+            __syncthreads();
+#pragma unroll 1
+            for (int ip = 0; ip < 2; ++ip) {
+                const int row0 = 8 * ip;
+                int* pvl = lp + row0;
+                if (SL > 1 && rows - row0 > NT) panel_factor_t<T, SL, NW>(PB, 16, rows, row0, tid, candk, candrow, pvl, info_sh, 16 * j);
+                else panel_factor_t<T, 1, NW>(PB, 16, rows, row0, tid, candk, candrow, pvl, info_sh, 16 * j);
+                __syncthreads();
+                if (tid < row0) {                                // the exchanges also apply to the multipliers of the first inner panel
+                    const int c = tid, cbase = c & ~7, cin = c & 7;
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const int P = pvl[q], Tg = row0 + q;
+                        if (P != Tg) {
+                            T* x = PB + Tg * 16 + cbase + (cin ^ swz(q));
+                            T* y = PB + P * 16 + cbase + (cin ^ swz(P & 7));
+                            const T tmp = *x; *x = *y; *y = tmp;
+                        }
+                    }
+                }
+                if (ip == 0) {
+                    if (tid < 8) stepb_column_t<T>(PB, 16, 0, 8 + tid, pvl);
+                    __syncthreads();
+                    const int ntl = rows / 8 - 1;
+                    const T b0 = PB[8 + fop.b0], b1 = PB[8 + fop.b1];
+                    for (int ti = warp; ti < ntl; ti += NW) {
+                        T* rowp = PB + (8 * (1 + ti) + g) * 16;
+                        const T a0 = rowp[fop.a0], a1 = rowp[fop.a1];
+                        Acc<T> v;
+                        v.set(0, rowp[8 + fop.c0]); v.set(1, rowp[8 + fop.c1]);
+                        v.mma1(a0, b0); v.mma2(a0, b0);
+                        v.mma1(a1, b1); v.mma2(a1, b1);
+                        rowp[8 + fop.c0] = v.get(0); rowp[8 + fop.c1] = v.get(1);
+                    }
+                    __syncthreads();
+                }
+            }
+            __syncthreads();
+            // ---- STORE: perm, multipliers (by original row), inverses of the diagonal blocks ----
+            if (tid == 0) {
+                for (int c = 0; c < 16; ++c) { const int P = 16 * j + lp[c]; const int tmp = perm[16 * j + c]; perm[16 * j + c] = perm[P]; perm[P] = tmp; }
+            }
+            __syncthreads();
+            for (int e = tid; e < (rows - 16) * 16; e += NT) {
+                const int lr = 16 + (e >> 4), c = e & 15;
+                const int o = perm[16 * j + lr];
+                Lg[((long long)j * R + o) * 16 + c] = PB[mphys(lr, c, 16)];
+            }
+            if (tid < 32) {
+                const int c = tid & 15;
+                T x[16];
+                if (tid < 16) {                                  // column c of (I - S)^-1, S = stored (negated) multipliers of L11
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        T acc = (i == c) ? Num<T>::one() : Num<T>::zero();
+#pragma unroll
+                        for (int k = 0; k < i; ++k) Num<T>::fma_(acc, PB[mphys(i, k, 16)], x[k]);
+                        x[i] = acc;
+                    }
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) { LIg[(long long)j * 256 + afrag_off(i, c)] = x[i]; xch[afrag_off(i, c)] = x[i]; }
+                } else {                                         // column c of U11^-1 (reciprocal pivots on the stored diagonal)
+#pragma unroll
+                    for (int i = 15; i >= 0; --i) {
+                        T acc = (i == c) ? Num<T>::one() : Num<T>::zero();
+#pragma unroll
+                        for (int k = i + 1; k < 16; ++k) Num<T>::fma_(acc, Num<T>::neg(PB[mphys(i, k, 16)]), x[k]);
+                        x[i] = Num<T>::mul(acc, PB[mphys(i, i, 16)]);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) UIg[(long long)j * 256 + afrag_off(i, c)] = x[i];
+                }
+            }
+            __syncthreads();
+            // ---- L~: rows of the finished block j in the earlier panels k < j are multiplied by L_jj^-1, in place ----
+            for (int k = warp; k < j; k += NW) {
+                T* Lk = Lg + (long long)k * R * 16;
+                T bq[4][2];
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+                    const T* rowp = Lk + (long long)perm[16 * j + 4 * kk + tl] * 16;
+                    bq[kk][0] = rowp[g]; bq[kk][1] = rowp[8 + g];
+                }
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    Acc<T> d0, d1;
+                    d0.zero(); d1.zero();
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk) {
+                        if (kk < 2 || h == 1) {
+                            const T a = xch[((h * 4 + kk) << 5) + lane];
+                            d0.mma1(a, bq[kk][0]); d1.mma1(a, bq[kk][1]);
+                            d0.mma2(a, bq[kk][0]); d1.mma2(a, bq[kk][1]);
+                        }
+                    }
+                    T* rowp = Lk + (long long)perm[16 * j + 8 * h + g] * 16 + 2 * tl;
+                    rowp[0] = d0.get(0); rowp[1] = d0.get(1);
+                    rowp[8] = d1.get(0); rowp[9] = d1.get(1);
+                }
+            }
+            __syncthreads();
+        }
+
+        // ---- back substitution: x_k = U_kk^-1 (y_k - sum_{k' > k} U[k, k'] x_k'), blocks from the last to the first ----
+        // block b belongs to warp b mod NW; its two row tiles of y are read back from the shared slots (B-fragment order)
+        __syncthreads();
+#pragma unroll
+        for (int bi = 0; bi < RBW; ++bi) {
+            const int b = warp + bi * NW;
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+#pragma unroll
+                for (int ct = 0; ct < 2; ++ct)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e)
+                        if (2 * bi + h < TPW) C[2 * bi + h][ct].set(e, b < nb ? BC[b * 256 + bfrag_off(8 * h + g, 8 * ct + 2 * tl + e)] : Num<T>::zero());
+        }
+        __syncthreads();
+        for (int k = nb - 1; k >= 0; --k) {
+#pragma unroll
+            for (int bi = 0; bi < RBW; ++bi) {
+                if (warp + bi * NW == k && 2 * bi + 1 < TPW) {   // x_k = U_kk^-1 (upper triangular inverse) times the finished block
+#pragma unroll
+                    for (int h = 0; h < 2; ++h)
+#pragma unroll
+                        for (int ct = 0; ct < 2; ++ct)
+#pragma unroll
+                            for (int e = 0; e < 2; ++e) xch[bfrag_off(8 * h + g, 8 * ct + 2 * tl + e)] = C[2 * bi + h][ct].get(e);
+                    __syncwarp();
+                    const T* ui = UIg + (long long)k * 256 + lane;
+                    T* slot = BC + k * 256;
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        Acc<T> d0, d1;
+                        d0.zero(); d1.zero();
+#pragma unroll
+                        for (int kk = 0; kk < 4; ++kk) {
+                            if (h == 0 || kk >= 2) {
+                                const T a = ui[(h * 4 + kk) << 5];
+                                const T b0 = xch[((kk * 2) << 5) + lane], b1 = xch[((kk * 2 + 1) << 5) + lane];
+                                d0.mma1(a, b0); if (mct > 1) d1.mma1(a, b1);
+                                d0.mma2(a, b0); if (mct > 1) d1.mma2(a, b1);
+                            }
+                        }
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            slot[bfrag_off(8 * h + g, 2 * tl + e)] = d0.get(e);
+                            slot[bfrag_off(8 * h + g, 8 + 2 * tl + e)] = d1.get(e);
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+            const T* Xk = BC + k * 256 + lane;
+#pragma unroll
+            for (int bi = 0; bi < RBW; ++bi) {
+                const int b = warp + bi * NW;
+                if (b < k && 2 * bi + 1 < TPW) {
+                    const T* ub = Ug + ((long long)b * nb + k) * 256 + lane;
+#pragma unroll
+                    for (int h = 0; h < 2; ++h)
+#pragma unroll
+                        for (int kk = 0; kk < 4; ++kk) {
+                            const T a = Num<T>::neg(ub[(h * 4 + kk) << 5]);
+                            const T b0 = Xk[(kk * 2) << 5], b1 = Xk[(kk * 2 + 1) << 5];
+                            C[2 * bi + h][0].mma1(a, b0); if (mct > 1) C[2 * bi + h][1].mma1(a, b1);
+                            C[2 * bi + h][0].mma2(a, b0); if (mct > 1) C[2 * bi + h][1].mma2(a, b1);
+                        }
+                }
+            }
+        }
+        __syncthreads();
+        // ---- outputs: x (position k = original unknown k: there is no column pivoting), Z = j zs x^T (cb Br) -> S ----
+        auto xs = [&](const int i, const int c) -> T { return BC[(i >> 4) * 256 + bfrag_off(i & 15, c)]; };
+        if (p.X) for (int e = tid; e < r * m; e += NT) { const int i = e / m, c = e - i * m; p.X[pt * (long long)r * m + e] = xs(i, c); }
+        if (p.info && tid == 0) p.info[pt] = *info_sh;
+        if (p.S) {
+            for (int e = warp; e < m * m; e += NW) {
+                const int a = e / m, b = e - a * m;
+                T acc = Num<T>::zero();
+                for (int k = lane; k < r; k += 32) Num<T>::fma_(acc, xs(k, a), Num<T>::scale(cb, __ldg(p.Br + (long long)k * p.ldb + b)));
+                acc = warp_sum(acc);
+                if (lane == 0) p.S[pt * (long long)m * m + e] = Num<T>::jz(p.zs[pt], acc);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+
 struct LeftGeom { int R, nb, NW, RBW, MINB; size_t smem, slot_elems; int cfg; };
 
 // Geometry per size (cfg): warps per CTA x owned 16-row blocks per warp must cover R / 16 blocks.
@@ -633,25 +1062,26 @@ LeftGeom left_geom(int r, int m) {
     gm.cfg = cfg;
     constexpr int NSTAGE = 2;
     gm.smem = sizeof(T) * ((size_t)gm.R * 16 + (size_t)gm.NW * NSTAGE * 128 + 256 + 2 * (size_t)gm.NW * 8) + sizeof(CandKeyL) * 2 * gm.NW
-            + sizeof(int) * ((size_t)gm.R + 16 + 4) + 64;
+            + sizeof(int) * ((size_t)gm.R + (size_t)gm.R / 8 + 16 + 4) + 64;
     gm.slot_elems = (size_t)gm.nb * gm.R * 16 + (size_t)gm.nb * gm.nb * 256 + 2 * (size_t)gm.nb * 256;
     (void)m;
     return gm;
 }
 
-template <typename T, int NW, int RBW, int MINB>
-int left_occupancy(const LeftGeom& gm, int* per_sm) {
-    auto kern = sweep_left_kernel<T, NW, RBW, MINB, 2>;
+template <typename K>
+int left_occupancy(K kern, int threads, const LeftGeom& gm, int* per_sm) {
     MF_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gm.smem));
-    MF_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, kern, NW * 32, gm.smem));
+    MF_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, kern, threads, gm.smem));
     return 0;
 }
 
 template <typename T, int NW, int RBW, int MINB>
 int launch_left(SweepParamsL<T> p, const LeftGeom& gm, size_t ws_bytes, cudaStream_t stream) {
-    auto kern = sweep_left_kernel<T, NW, RBW, MINB, 2>;
+    // the first version of the kernel body stays the default until the second one has passed the parity suite on hardware
+    static const bool v1 = getenv("MF_LEFT_V2") == nullptr;
+    auto kern = v1 ? sweep_left_kernel<T, NW, RBW, MINB, 2> : sweep_left2_kernel<T, NW, 2 * RBW, MINB, 2>;
     int per_sm = 0;
-    if (int rc = left_occupancy<T, NW, RBW, MINB>(gm, &per_sm)) return rc;
+    if (int rc = left_occupancy(kern, NW * 32, gm, &per_sm)) return rc;
     if (per_sm < 1) MF_FAIL_ARG(7, "left-looking sweep does not fit on an SM for this (r, m)");
     const size_t slot = sizeof(T) * gm.slot_elems;
     long long grid = (long long)mf_num_sms() * per_sm;

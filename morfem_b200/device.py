@@ -365,6 +365,74 @@ def spmm(a: DeviceCSR, q: torch.Tensor, out: Optional[torch.Tensor] = None, col_
     return out
 
 
+@dataclass
+class DeviceWindows:
+    """Operand of the TMA-staged SpMM (mf_spmm_window_*): CSR rows in blocks of RB with, per block, the list of distinct
+    Q rows it references (the window) and, per non-zero, the 8-bit slot of its column inside that window."""
+    rowptr: torch.Tensor    # int32, nrows + 1
+    slot: torch.Tensor      # uint8, nnz
+    vals: torch.Tensor      # float64, nnz
+    wstart: torch.Tensor    # int32, nblocks + 1
+    ucol: torch.Tensor      # int32, sum of window sizes
+    nrows: int
+    wmax: int
+    nnz: int
+
+
+def build_windows(a_csc, device=None, row_range=None, col_offset: int = 0) -> Optional[DeviceWindows]:
+    """Window lists for the TMA-staged SpMM, built once per operator on the host (numpy): for every block of RB rows of
+    ``a.T`` the sorted distinct column indices, and for every non-zero its position in its block's list.  Returns None when
+    the operator does not qualify (complex values, a window above mf_spmm_window_max_rows(), a row with too many non-zeros)."""
+    import scipy.sparse as sp
+    lib = _ffi.load()
+    device = device or require_cuda()
+    a = a_csc if sp.issparse(a_csc) and a_csc.format == "csc" else sp.csc_array(a_csc)
+    if np.iscomplexobj(a.data):
+        return None
+    rb = int(lib.mf_spmm_window_rows_per_block())
+    lo, hi = (0, a.shape[1]) if row_range is None else row_range
+    indptr = np.asarray(a.indptr)
+    s, e = int(indptr[lo]), int(indptr[hi])
+    rowptr = (indptr[lo:hi + 1] - indptr[lo]).astype(np.int64)
+    cols = np.asarray(a.indices[s:e]).astype(np.int64) - col_offset
+    nrows = hi - lo
+    counts = np.diff(rowptr)
+    if nrows == 0 or counts.max(initial=0) > int(lib.mf_spmm_window_max_nnz_per_row()):
+        return None
+    nblocks = (nrows + rb - 1) // rb
+    blk = np.repeat(np.arange(nrows, dtype=np.int64) // rb, counts)
+    ncols = int(a.shape[0])
+    key = blk * ncols + cols
+    ukey, inv = np.unique(key, return_inverse=True)
+    ublk = ukey // ncols
+    wstart = np.searchsorted(ublk, np.arange(nblocks + 1, dtype=np.int64)).astype(np.int64)
+    wmax = int(np.diff(wstart).max(initial=0))
+    if wmax > int(lib.mf_spmm_window_max_rows()):
+        return None
+    slot = (inv - wstart[blk]).astype(np.uint8)
+    return DeviceWindows(upload(np.ascontiguousarray(rowptr.astype(np.int32)), device), upload(np.ascontiguousarray(slot), device),
+                         upload(np.ascontiguousarray(a.data[s:e], dtype=np.float64), device),
+                         upload(np.ascontiguousarray(wstart.astype(np.int32)), device),
+                         upload(np.ascontiguousarray((ukey % ncols).astype(np.int32)), device), nrows, max(wmax, 1), int(e - s))
+
+
+def spmm_window(a: DeviceWindows, q: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``Y = A Q`` through the TMA-staged kernel (Q row windows fetched into shared memory by bulk asynchronous copies)."""
+    lib = _ffi.load()
+    _check_mat(q, "q")
+    r = q.shape[1]
+    real = q.dtype == F64
+    if out is None:
+        out = torch.empty((a.nrows, r), dtype=q.dtype, device=q.device)
+    w = 8.0 if real else 16.0
+    fn = lib.mf_spmm_window_f64 if real else lib.mf_spmm_window_c128
+    with _timed("spmm_window", nbytes=a.nnz * 9.0 + 4.0 * (a.nrows + 1) + 4.0 * a.ucol.numel() + w * r * (a.nrows + q.shape[0]),
+                flops=(2.0 if real else 4.0) * a.nnz * r):
+        _ffi.check(fn(_ptr(a.rowptr), _ptr(a.slot), _ptr(a.vals), _ptr(a.wstart), _ptr(a.ucol), a.nrows, a.wmax, _ptr(q), q.stride(0), r,
+                      _ptr(out), out.stride(0), _stream()), "mf_spmm_window")
+    return out
+
+
 # The two-operator kernel walks the plain CSR pattern.  Measured on B200: r = 64 one pass 0.37 ms against 2 x 0.28 ms (row-grouped,
 # G = 4); r = 256 1.10 ms against 2 x 0.46 ms (row-grouped, G = 2) -- the callers use it up to this basis size only.
 SPMM2_MAX_R = 128

@@ -144,6 +144,44 @@ def scattering_sweep(frequency_points, x: np.ndarray, b_reduced: np.ndarray,
     return gsm
 
 
+# ------------------------------------------------------------------------ greedy residual estimator (row N1)
+def error_estimator(q: np.ndarray, domain, a0, a1, a2, b,
+                    t_a0: Callable, t_a1: Callable, t_a2: Callable, t_b: Callable) -> np.ndarray:
+    """implementation.py:348-452 with ``USE_OPM = False`` (the default, :16): per point the Frobenius norm of the 16-term
+    expansion of ``(A(t) q x - t_b b)^H (A(t) q x - t_b b)`` built from the sparse products ``h(a_i) @ a_j`` (:370-385),
+    their projections (:387-402) and the reduced solve (:404-415).  Sparse operands as in the reference."""
+    def hh(m):
+        return m.conj().T                                       # h(), :483-488
+
+    ops = (a0, a1, a2)
+    aha = [[hh(ops[i]) @ ops[j] for j in range(3)] for i in range(3)]          # :370-381
+    ahb = [hh(ops[i]) @ b for i in range(3)]                                   # :373, :377, :381
+    bha = [hh(b) @ ops[i] for i in range(3)]                                   # :382-384
+    bh_b = hh(b) @ b                                                           # :385
+    qh = hh(q)
+    g = [[qh @ aha[i][j] @ q for j in range(3)] for i in range(3)]             # :387-398
+    hb = [qh @ ahb[i] for i in range(3)]
+    bq = [bha[i] @ q for i in range(3)]                                        # :399-401
+    dense = lambda m: m.toarray() if hasattr(m, "toarray") else np.asarray(m)  # noqa: E731
+    hb, bq, bh_b = [dense(m) for m in hb], [dense(m) for m in bq], dense(bh_b)
+    a0_r, a1_r, a2_r, b_r = galerkin_projection(q, a0, a1, a2, b)              # :404-409
+    domain = np.asarray(domain)
+    err = np.empty(domain.size)
+    for i in range(domain.size):
+        t = domain[i]
+        c = (t_a0(t), t_a1(t), t_a2(t))
+        tb = t_b(t)
+        x = solve_point(c[0], c[1], c[2], tb, a0_r, a1_r, a2_r, b_r)            # :415
+        x_h = hh(x)
+        e = tb * tb * bh_b                                                     # :424-441, same 16 terms
+        for ia in range(3):
+            for ib in range(3):
+                e = e + c[ia] * c[ib] * x_h @ g[ia][ib] @ x
+            e = e - c[ia] * tb * x_h @ hb[ia] - tb * c[ia] * bq[ia] @ x
+        err[i] = np.linalg.norm(e)
+    return err
+
+
 # ------------------------------------------------------------------------------------------ whole path
 def hot_path(snapshots, domain, a0, a1, a2, b,
              t_a0=lambda t: 1.0, t_a1=lambda t: t, t_a2=lambda t: t ** 2, t_b=b_coefficient,

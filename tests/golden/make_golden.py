@@ -16,6 +16,10 @@ Cases
                     block, so lines 178-186 (projection + reduced sweep) run verbatim; then the GSM loop.
   equidist_n600     ``USE_EQUALLY_DISTRIBUTED = True`` path (``implementation.py:197-214``) end to end.
   reduced_rXX_mY    ``solve_finite_element_method`` + ``generalized_scattering_matrix`` on seeded reduced models.
+  estimator_n600    ``implementation.error_estimator`` (:348-452) itself, called on the orthonormalised bases a greedy run
+                    passes through (r = 4, 6, 8, 10; 2 ports) and on a 3-port model: the per-point residual estimate the
+                    greedy search takes its arg-max of, plus the size of the largest term of the 16-term sum (the estimate
+                    is a difference of terms of that size, so it is only defined to eps times it).
 """
 from __future__ import annotations
 
@@ -157,10 +161,40 @@ def case_reduced(r, m, npts, seed):
          x=x, gsm=gsm, cond=cond)
 
 
+def case_estimator():
+    out = {}
+    for tag, ports in (("p2", 2), ("p3", 3)):
+        ct, tt = synthetic.waveguide_operators(5, 4, 30)
+        n = ct.shape[0]
+        wp = synthetic.port_matrix(n, ports, 19)
+        in_c, in_gamma, in_b = synthetic.driver_scaled(ct, tt, wp)
+        f = np.linspace(3e9, 5e9, 60)
+        md = ref_impl.ModelDefinition(f, in_c, csc_array(in_c.shape), in_gamma, in_b, lambda t: 1, lambda t: t,
+                                      lambda t: t ** 2, lambda t: ref_help.b_coefficient(t))
+        # the bases of a greedy run (implementation.py:222-226, :297-298): end points first, then the arg-max points
+        q = np.linalg.svd(np.hstack((ref_impl.solve_fem_point(f[0], md), ref_impl.solve_fem_point(f[-1], md))),
+                          full_matrices=False)[0]
+        for it in range(4 if ports == 2 else 2):
+            err = quiet(ref_impl.error_estimator, md, q, ref_impl.OfflinePhaseMatrices(), ref_impl.TimeStatistics())
+            bh_b = (in_b.T @ in_b).toarray()
+            scale = np.array([ref_help.b_coefficient(t) ** 2 for t in f]) * np.linalg.norm(bh_b)
+            out[f"{tag}_q{it}"] = q
+            out[f"{tag}_err{it}"] = err
+            out[f"{tag}_scale{it}"] = scale
+            q_new = ref_impl.solve_fem_point(f[int(err.argmax())], md)
+            q = np.linalg.svd(np.hstack((q, q_new)), full_matrices=False)[0]
+        out[f"{tag}_f"] = f
+    save("estimator_n600", grid=np.array([5, 4, 30]), face=np.array(19), **out)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "estimator":
+        case_estimator()
+        sys.exit(0)
     case_cfg1()
     case_stages()
     case_equidist()
     for r, m, npts, seed in [(8, 2, 64, 1), (24, 4, 48, 2), (33, 3, 24, 6), (64, 2, 64, 3), (96, 3, 16, 4), (160, 4, 8, 5),
                              (256, 4, 4, 7)]:
         case_reduced(r, m, npts, seed)
+    case_estimator()

@@ -314,3 +314,30 @@ def test_gram_matrices_use_the_symmetric_tile_path(dv, n, r):
     # a plain transpose of the same operand (conj=False, complex) is NOT Hermitian and must take the general path
     gt = dv.gemm_tn(ad, ad, conj=False).cpu().numpy()
     assert rel(gt, a.T @ a) < 1e-13
+
+
+@pytest.mark.parametrize("real", [False, True])
+@pytest.mark.parametrize("grid,r", [((5, 4, 30), 6), ((6, 5, 40), 64), ((7, 3, 50), 100), ((4, 4, 33), 256)])
+def test_tma_window_spmm_matches_scipy(real, grid, r):
+    """mf_spmm_window_*: Q row windows staged in shared memory by bulk asynchronous copies (the north star's TMA variant of the
+    stage-2 SpMM) against scipy's own product (implementation.py:181-183), including a row range with window-relative
+    column indices (the multi-GPU halo layout) and a ragged last block."""
+    from morfem_b200 import device as dv, synthetic
+    dev = dv.require_cuda()
+    ct, tt = synthetic.waveguide_operators(*grid)
+    n = ct.shape[0]
+    rng = np.random.default_rng(r)
+    q = rng.standard_normal((n, r)) if real else rng.standard_normal((n, r)) + 1j * rng.standard_normal((n, r))
+    qd = torch.from_numpy(q).to(dev)
+    for a in (ct, tt):
+        win = dv.build_windows(a, dev)
+        assert win is not None and win.wmax <= 9 * (8 + 2)
+        y = dv.spmm_window(win, qd).cpu().numpy()
+        ref = a.T @ q
+        assert np.linalg.norm(y - ref) <= 1e-13 * np.linalg.norm(ref)
+        lo, hi = n // 3 + 1, n - 5                                   # a row shard with a halo window, not a multiple of 8 rows
+        from morfem_b200 import dist as mfd
+        w0, w1 = mfd.column_window(np.asarray(a.indptr), np.asarray(a.indices), lo, hi, n)
+        win = dv.build_windows(a, dev, row_range=(lo, hi), col_offset=w0)
+        y = dv.spmm_window(win, qd[w0:w1].contiguous()).cpu().numpy()
+        assert np.linalg.norm(y - ref[lo:hi]) <= 1e-13 * np.linalg.norm(ref[lo:hi])

@@ -413,3 +413,28 @@ def test_basis_size_study_config4(dv):
     for eg, ec in zip(errs_gpu, errs_cpu):
         assert abs(eg - ec) <= 0.05 * ec + 5e-10, (errs_gpu, errs_cpu)      # same error curve (7e-6, 2e-8, 7e-11, ... on the CPU)
     assert errs_gpu[0] > errs_gpu[1] > errs_gpu[2] and errs_gpu[-1] < 1e-9
+
+
+def test_error_estimator_matches_live_reference_values():
+    """``error_estimator`` (implementation.py:348-452) evaluated on the device -- Gram matrices of the SpMM
+    outputs instead of the reference's sparse-sparse products, the reduced sweep, ``mf_estimator_c128`` -- against the
+    per-point estimates of the LIVE reference on the bases of a greedy run (tests/golden/estimator_n600.npz).  1e-8 relative
+    where the estimate is above its own cancellation floor (a few eps times the size of the largest of its 16 terms), and
+    the greedy search's arg-max point must agree."""
+    from scipy.sparse import csc_array
+    from morfem_b200 import implementation as impl, test_helpers as th, synthetic
+    g = np.load(os.path.join(GOLDEN, "estimator_n600.npz"))
+    eps = np.finfo(float).eps
+    for tag, ports, iters in (("p2", 2, 4), ("p3", 3, 2)):
+        ct, tt = synthetic.waveguide_operators(*(int(v) for v in g["grid"]))
+        wp = synthetic.port_matrix(ct.shape[0], ports, int(g["face"]))
+        in_c, in_gamma, in_b = synthetic.driver_scaled(ct, tt, wp)
+        f = g[tag + "_f"]
+        md = impl.ModelDefinition(f, in_c, csc_array(in_c.shape), in_gamma, in_b, lambda t: 1, lambda t: t, lambda t: t ** 2,
+                                  lambda t: th.b_coefficient(t))
+        for it in range(iters):
+            err = impl.error_estimator(md, g[f"{tag}_q{it}"])
+            ref, scale = g[f"{tag}_err{it}"], g[f"{tag}_scale{it}"]
+            assert err.shape == ref.shape
+            assert np.all(np.abs(err - ref) <= 1e-8 * ref + 200 * eps * scale), (tag, it, float(np.abs(err - ref).max()))
+            assert int(err.argmax()) == int(ref.argmax())

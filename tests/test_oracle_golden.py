@@ -131,3 +131,24 @@ def test_comparison_helpers():
     a_r = q.T @ a @ q
     q2 = q @ np.linalg.qr(rng.standard_normal((6, 6)))[0]
     assert orc.rel_err(orc.align_reduced(a_r, q, q2), q2.T @ a @ q2) < 1e-13
+
+
+def test_error_estimator_matches_live_reference(golden_dir):
+    """The oracle's restatement of implementation.py:348-452 against the per-point estimates of the live reference, on
+    the bases a greedy run passes through.  The estimate is a difference of terms of size ``scale``: it is defined to a few
+    eps * scale, which is all that is left at the snapshot points themselves."""
+    from scipy.sparse import csc_array
+    from morfem_b200 import synthetic
+    g = np.load(os.path.join(golden_dir, "estimator_n600.npz"))
+    eps = np.finfo(float).eps
+    for tag, ports, iters in (("p2", 2, 4), ("p3", 3, 2)):
+        ct, tt = synthetic.waveguide_operators(*(int(v) for v in g["grid"]))
+        wp = synthetic.port_matrix(ct.shape[0], ports, int(g["face"]))
+        in_c, in_gamma, in_b = synthetic.driver_scaled(ct, tt, wp)
+        f = g[tag + "_f"]
+        for it in range(iters):
+            err = orc.error_estimator(g[f"{tag}_q{it}"], f, in_c, csc_array(in_c.shape), in_gamma, in_b,
+                                      lambda t: 1, lambda t: t, lambda t: t ** 2, orc.b_coefficient)
+            ref, scale = g[f"{tag}_err{it}"], g[f"{tag}_scale{it}"]
+            assert np.all(np.abs(err - ref) <= 1e-10 * ref + 50 * eps * scale), (tag, it, np.abs(err - ref).max())
+            assert int(err.argmax()) == int(ref.argmax())

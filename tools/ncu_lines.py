@@ -19,8 +19,14 @@ stall_cols = [n for n in hdr if n.startswith("stall_") and "Not Issued" not in n
 m = re.search(r"(\w+)<(.*)>\(", kernel_full)
 frag = kname
 if m:
-    args = re.findall(r"\(int\)(\d+)|\(bool\)(\d+)", m.group(2))
-    frag = m.group(1) + "I" + "".join(("Li%sE" % a) if a else ("Lb%sE" % b) for a, b in args)
+    parts = []
+    for a in [x.strip() for x in m.group(2).split(",")]:
+        mi = re.match(r"\(int\)(\d+)$", a); mb = re.match(r"\(bool\)(\d+)$", a)
+        if mi: parts.append("Li%sE" % mi.group(1))
+        elif mb: parts.append("Lb%sE" % mb.group(1))
+        elif a == "double": parts.append("d")
+        else: parts.append("%d%s" % (len(a), a))          # a named type, e.g. double2 -> 7double2
+    frag = m.group(1) + "I" + "".join(parts)
 linemap = {}
 for f in os.listdir(tmp):
     if not f.endswith(".cubin"): continue
