@@ -694,6 +694,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
+    ap.add_argument("--r", type=int, default=0, help="override the basis size of the workload (BASELINE configs[3]: r = 16..512 at N = 1M)")
+    ap.add_argument("--points", type=int, default=0, help="override the number of sweep points of the workload")
+    ap.add_argument("--ports", type=int, default=0, help="override the number of ports of the workload")
     ap.add_argument("--cpu-points", type=int, default=0, help="sweep points the CPU legs solve (scaled to the full axis); 0 = per workload")
     ap.add_argument("--cpu-rows", type=int, default=62500, help="rows of the snapshot block / operators the reference arm's stages 1+2 run on per step")
     ap.add_argument("--parity", default="auto", choices=["auto", "full", "isolated"],
@@ -707,7 +710,10 @@ def main():
     ap.add_argument("--no-alt-dtype", action="store_true", help="skip the second timed loop on the other arithmetic type")
     ap.add_argument("--no-graph", action="store_true", help="run the eager (adaptive CholeskyQR) step instead of the CUDA-graph replay")
     args = ap.parse_args()
-    wl = WORKLOADS[args.workload]
+    wl = dict(WORKLOADS[args.workload])
+    if args.r or args.points or args.ports:
+        wl["r"], wl["f"], wl["m"] = args.r or wl["r"], args.points or wl["f"], args.ports or wl["m"]
+        wl["desc"] += f" [overridden: r={wl['r']}, {wl['m']} ports, {wl['f']} points -- BASELINE configs[3], basis-size sweep]"
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

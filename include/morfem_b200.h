@@ -105,7 +105,8 @@ int mf_spmm_csr2_f64(const int32_t* rowptr, const int32_t* colidx, const double*
  * Build once per operator: counts[g] = union size of group g (mf_spmm_group_count); ustart = exclusive prefix sum of
  * counts (int64, ngroups + 1 entries, caller computed); mf_spmm_group_fill writes ucols[ustart[g] + k] and
  * uvals[(ustart[g] + k) * G + i] (coefficient of row g*G + i, 0 when absent).  Then mf_spmm_grouped_c128 == mf_spmm_csr_c128. */
-int mf_spmm_group_size(int r);
+int mf_spmm_group_size(int r);       /* complex128 Q: 4 rows up to r = 128, 2 above */
+int mf_spmm_group_size_f64(int r);   /* float64 Q: 4 rows up to r = 256, 2 above */
 int mf_spmm_group_count(const int32_t* rowptr, const int32_t* colidx, int64_t nrows, int G, int32_t* counts, void* stream);
 int mf_spmm_group_fill(const int32_t* rowptr, const int32_t* colidx, const double* vals, int64_t nrows, int G,
                        const int64_t* ustart, int32_t* ucols, double* uvals, void* stream);

@@ -45,6 +45,7 @@ SIGNATURES = {
     "mf_spmm_csr2_f64": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int, c_void_p, c_int64,
                                  c_void_p, c_int64, c_void_p]),
     "mf_spmm_group_size": (c_int, [c_int]),
+    "mf_spmm_group_size_f64": (c_int, [c_int]),
     "mf_spmm_group_count": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p]),
     "mf_spmm_group_fill": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "mf_spmm_grouped_c128": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_int64, c_int, c_void_p, c_int64,

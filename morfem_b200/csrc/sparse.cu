@@ -449,15 +449,11 @@ extern "C" int mf_project_rhs_c128(const int32_t* colptr, const int32_t* rowidx,
     return 0;
 }
 
-// Rows per group.  Four rows share one column-union list (a Q row is pulled through L1 once for four output rows); above
-// r = 128 the accumulators of four full rows no longer fit the register file, so the complex kernel runs column slices of
-// 128 (blockIdx.y) instead of falling back to two rows per group.  MF_SPMM_SPLIT=0 restores the round-1 policy (2 rows, full width).
-static bool spmm_split_mode() {
-    static int mode = -1;
-    if (mode < 0) { const char* e = getenv("MF_SPMM_SPLIT"); mode = (e && atoi(e) == 0) ? 0 : 1; }
-    return mode == 1;
-}
-extern "C" int mf_spmm_group_size(int r) { return (r <= 128 || spmm_split_mode()) ? 4 : 2; }
+// Rows per group (measured on B200, N = 1M, r = 256, profiles/r02_spmm.md): complex128 -- four rows up to r = 128, two above
+// (four rows in column slices of 128 read every index and coefficient list twice and lost: 7.6 ms against 3.5 ms); float64 --
+// four rows up to r = 256 (the accumulators of four rows of 256 real columns fit: 2.67 ms against 3.05 ms for two rows).
+extern "C" int mf_spmm_group_size(int r) { return r <= 128 ? 4 : 2; }
+extern "C" int mf_spmm_group_size_f64(int r) { return r <= 256 ? 4 : 2; }
 
 extern "C" int mf_spmm_group_count(const int32_t* rowptr, const int32_t* colidx, int64_t nrows, int G, int32_t* counts, void* stream) {
     if (!rowptr) MF_FAIL_ARG(1, "rowptr is NULL");
@@ -547,7 +543,7 @@ extern "C" int mf_spmm_grouped_f64(const int64_t* ustart, const int32_t* ucols, 
     if (!uvals) MF_FAIL_ARG(3, "uvals is NULL");
     if (nrows < 0) MF_FAIL_ARG(4, "nrows < 0");
     if (r <= 0 || r > 512) MF_FAIL_ARG(8, "need 0 < r <= 512");
-    if (G != mf_spmm_group_size(r)) MF_FAIL_ARG(5, "group size must equal mf_spmm_group_size(r)");
+    if (G != mf_spmm_group_size_f64(r)) MF_FAIL_ARG(5, "group size must equal mf_spmm_group_size_f64(r)");
     if (!Q || ldq < r) MF_FAIL_ARG(6, "Q is NULL or ldq < r");
     if (!Y || ldy < r) MF_FAIL_ARG(9, "Y is NULL or ldy < r");
     if (nrows == 0) return 0;

@@ -805,7 +805,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) sweep_left2_kernel(SweepParamsL
                     if (ifirst >= imax) continue;                // no tile of this warp below block k any more
                     {                                            // wait for both halves of U[k, j]
                         volatile int* f = uflag + 2 * k;
-                        while (f[0] != epoch || f[1] != epoch) { }
+                        while (f[0] != epoch || f[1] != epoch) { __nanosleep(20); }
                         __threadfence_block();
                     }
                     const T* Uk = BC + k * 256 + lane;
@@ -1077,8 +1077,8 @@ int left_occupancy(K kern, int threads, const LeftGeom& gm, int* per_sm) {
 
 template <typename T, int NW, int RBW, int MINB>
 int launch_left(SweepParamsL<T> p, const LeftGeom& gm, size_t ws_bytes, cudaStream_t stream) {
-    // the first version of the kernel body stays the default until the second one has passed the parity suite on hardware
-    static const bool v1 = getenv("MF_LEFT_V2") == nullptr;
+    // MF_LEFT_V1 selects the first version of the kernel body (kept for A/B measurements)
+    static const bool v1 = getenv("MF_LEFT_V1") != nullptr;
     auto kern = v1 ? sweep_left_kernel<T, NW, RBW, MINB, 2> : sweep_left2_kernel<T, NW, 2 * RBW, MINB, 2>;
     int per_sm = 0;
     if (int rc = left_occupancy(kern, NW * 32, gm, &per_sm)) return rc;

@@ -304,12 +304,17 @@ def csr_of_transpose(a_csc, device=None, row_range=None, col_offset: int = 0, gr
     return csr
 
 
-def group_rows(a: DeviceCSR, r: int) -> None:
+def _group_size(r: int, real: bool) -> int:
+    lib = _ffi.load()
+    return int(lib.mf_spmm_group_size_f64(r) if real else lib.mf_spmm_group_size(r))
+
+
+def group_rows(a: DeviceCSR, r: int, real: bool = False) -> None:
     """Build the row-grouped form of a real CSR operand with sorted column indices on the device (once per operator and
-    group size): G = mf_spmm_group_size(r) consecutive rows share one column-union list, so the SpMM loads each needed
+    group size): G = mf_spmm_group_size(r) (mf_spmm_group_size_f64 for a float64 Q) consecutive rows share one column-union list, so the SpMM loads each needed
     Q row once per group.  No-op when already built for this G or when the values are complex."""
     lib = _ffi.load()
-    g = int(lib.mf_spmm_group_size(r))
+    g = _group_size(r, real)
     if not a.is_real or not a.sorted_indices or a.nrows == 0 or (a.grouped is not None and a.grouped[0] == g):
         return
     dev = a.colidx.device
@@ -337,7 +342,7 @@ def spmm(a: DeviceCSR, q: torch.Tensor, out: Optional[torch.Tensor] = None, col_
     if out is None:
         out = torch.empty((a.nrows, r), dtype=q.dtype, device=q.device)
     w = 8.0 if real else 16.0
-    if a.grouped is not None and col_offset == 0 and a.grouped[0] == int(lib.mf_spmm_group_size(r)):
+    if a.grouped is not None and col_offset == 0 and a.grouped[0] == _group_size(r, real):
         g, ustart, ucols, uvals = a.grouped
         nunion = (int(ustart[-1].item()) if timer is not None else 0)      # only the profiling pass needs the exact size
         if real:

@@ -382,7 +382,7 @@ class ShardedHotPath:
                 live = []
             for k, i in enumerate(live):
                 csr, plan = self.ops[i], self.plans[i]
-                dv.group_rows(csr, r)                # row-grouped operand, built once per operator on first use
+                dv.group_rows(csr, r, real=x.dtype == torch.float64)   # row-grouped operand, built once per operator (and element type)
                 if self.world > 1:
                     key = (plan.win0, plan.win1, tuple(plan.send), tuple(plan.recv))
                     if key not in windows:

@@ -200,7 +200,7 @@ class _DeviceOperators:
                 continue
             self.wait_ready(i)
             if self.grouped:
-                dv.group_rows(at, x.shape[1])
+                dv.group_rows(at, x.shape[1], real=x.dtype == dv.F64)
             g_list.append(dv.gemm_tn(dv.spmm(at, x), x, conj=False))
         self.wait_ready("b")
         return g_list, dv.project_rhs(self.b, x, 0, conj=False)

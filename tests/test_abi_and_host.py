@@ -61,7 +61,7 @@ def test_argument_validation_without_gpu():
     assert lib.mf_jacobi_svd_f64(None, 4, 4, None, 4, None, 10, 1e-15, None, None) == -1
     assert lib.mf_gemm_tn_f64_ws_bytes(64, 64, 100000) >= 64 * 64 * 8
     # shape support queries (host only): which kernel family serves which (r, m)
-    assert lib.mf_spmm_group_size(64) == 4 and lib.mf_spmm_group_size(256) == 4      # wide bases: column slices of 128, still four rows per group
+    assert lib.mf_spmm_group_size(64) == 4 and lib.mf_spmm_group_size(256) == 2 and lib.mf_spmm_group_size_f64(256) == 4
     assert lib.mf_sweep_f64_supported(64, 2) == 1 and lib.mf_sweep_f64_supported(256, 4) == 1 and lib.mf_sweep_f64_supported(513, 4) == 0
     assert lib.mf_sweep_f64_variant_supported(256, 4, 3) == 0 and lib.mf_sweep_f64_variant_supported(256, 4, 5) == 1
     assert lib.mf_sweep_f64_ws_bytes(64, 2, 1000, 0) == 256 and lib.mf_sweep_f64_ws_bytes(256, 4, 1000, 0) >= 148 * 2 * 256 * 256 * 8

@@ -254,7 +254,7 @@ def test_real_gemm_twins_match_numpy_and_the_complex_kernels(dv, n, ra, rb):
     assert rel(cs, wide[:, :ra].T @ wide[:, ra:ra + rb]) < 1e-14
 
 
-@pytest.mark.parametrize("r", [7, 64, 100, 200])
+@pytest.mark.parametrize("r", [7, 64, 100, 200, 256])
 def test_real_spmm_and_rhs_projection_twins(dv, r):
     from morfem_b200 import synthetic
     ct, _ = synthetic.waveguide_operators(6, 5, 41)
@@ -264,7 +264,8 @@ def test_real_spmm_and_rhs_projection_twins(dv, r):
     qd = torch.from_numpy(q).cuda()
     csr = dv.csr_of_transpose(ct)
     y_csr = dv.spmm(csr, qd).cpu().numpy()
-    dv.group_rows(csr, r)
+    dv.group_rows(csr, r, real=True)
+    assert csr.grouped is not None and csr.grouped[0] == 4       # float64: four rows per group up to r = 256
     y_grp = dv.spmm(csr, qd).cpu().numpy()
     ref = (q.T @ ct).T
     assert y_csr.dtype == np.float64 and rel(y_csr, ref) < 1e-14 and rel(y_grp, ref) < 1e-14

@@ -65,7 +65,7 @@ def test_sharded_arithmetic_emulated_on_one_gpu(world, real):
             win = x[plan.win0:plan.win1].contiguous()            # what the halo exchange assembles on this rank
             y = dv.spmm(csr, win)
             if rank == 1:
-                dv.group_rows(csr, r)                            # the row-grouped operand on a window as well
+                dv.group_rows(csr, r, real=real)                 # the row-grouped operand on a window as well
                 y2 = dv.spmm(csr, win)
                 assert torch.allclose(y, y2, rtol=1e-13, atol=0)
             proj[i] += dv.gemm_tn(y, x_loc, conj=False)
