@@ -93,6 +93,7 @@ struct SweepParamsL {
     cplx* S;      // F x m x m or NULL
     int* info;    // F or NULL
     T* ws; long long ws_stride;   // per-CTA workspace slots (elements)
+    unsigned long long* timing;   // debugging aid (MF_LEFT_TIMING): per-phase clock64 sums of CTA 0, or NULL
 };
 
 struct CandKeyL { double v; int pos; int pad; };
@@ -121,7 +122,15 @@ __device__ __forceinline__ int bfrag_off(int i, int c) { return (((i >> 2) * 2 +
 __device__ __forceinline__ int afrag_off(int i, int c) { return (((i >> 3) * 4 + (c >> 2)) << 5) + ((i & 7) << 2) + (c & 3); }
 
 // ---- inner panel factorisation by the whole CTA (8 columns; see sweep_stream.cu panel_factor_mw for the description) ------
-template <typename T, int SL, int NW>
+// barrier of the threads that factor the panel: the whole CTA (BARN = 0) or a named barrier of BARN threads (the look-ahead
+// version of the kernel factors the panel with half of the warps while the other half runs ahead)
+template <int BARN>
+__device__ __forceinline__ void csync() {
+    if (BARN == 0) __syncthreads();
+    else asm volatile("bar.sync 1, %0;" :: "n"(BARN) : "memory");
+}
+
+template <typename T, int SL, int NW, int BARN = 0>
 __device__ __forceinline__ void panel_factor_t(T* PB, const int LDp, const int rows, const int row0, const int tid,
                                                CandKeyL* candk, T* candrow, int* pvl, int* info_sh, const int info_base) {
     constexpr int NT = NW * 32;
@@ -130,7 +139,7 @@ __device__ __forceinline__ void panel_factor_t(T* PB, const int LDp, const int r
     const int nact = min(NW, (rows - row0 + 31) >> 5);
     if (warp >= nact) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) __syncthreads();
+        for (int j = 0; j < 8; ++j) csync<BARN>();
         return;
     }
     T a[SL][8];
@@ -182,7 +191,7 @@ __device__ __forceinline__ void panel_factor_t(T* PB, const int LDp, const int r
                     for (int c = 0; c < 8; ++c) cr[warp * 8 + c] = (c == j) ? rc : a[s][c];
                 }
         }
-        __syncthreads();
+        csync<BARN>();
         // global winner among the NW warp candidates: lane w looks at candidate w, then the same warp arg-max
         double cv = -2.0; int cp = 0x7fffffff;
         if (lane < nact) {
@@ -269,356 +278,10 @@ __device__ __forceinline__ void stepb_column_t(T* M, const int LD, const int row
     for (int j = 1; j < 8; ++j) colp[j * LD + (cin ^ swz(j))] = u[j];
 }
 
-// ---- the kernel ------------------------------------------------------------------------------------------------------
-// NW warps; warp w owns the 16-row blocks w, w + NW, ... (RBW of them at most); MINB CTAs per SM (register budget);
-// NSTAGE = depth of the per-lane FIFO of L fragments.
-template <typename T, int NW, int RBW, int MINB, int NSTAGE>
-__global__ void __launch_bounds__(NW * 32, MINB) sweep_left_kernel(SweepParamsL<T> p, int R) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    constexpr int NT = NW * 32;
-    constexpr int SL = (RBW + 1) / 2;                            // rows per thread in the panel factorisation (R <= 16 NW RBW)
-    constexpr bool CACHE_B = sizeof(T) == 8;                     // real twin: keep the U fragments of a step in registers
-    const int r = p.r, m = p.m, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int g = lane >> 2, t = lane & 3;
-    const int nb = R >> 4;                                       // 16-row / 16-column blocks
-    const int mct = (m + 7) >> 3;                                // column tiles of the right-hand-side block column
-
-    T* BC = reinterpret_cast<T*>(smem_raw);                      // R x 16: U blocks (fragment order) | panel rows (swizzled)
-    T* ring = BC + (size_t)R * 16;                               // NW x NSTAGE x 128: per-lane FIFO of L fragments
-    T* xch = ring + (size_t)NW * NSTAGE * 128;                   // 256: C-layout -> B-fragment exchange of a chain link
-    T* candrow = xch + 256;                                      // 2 x NW x 8
-    CandKeyL* candk = reinterpret_cast<CandKeyL*>(candrow + 2 * NW * 8);   // 2 x NW
-    int* perm = reinterpret_cast<int*>(candk + 2 * NW);          // R: position -> original row
-    int* lp = perm + R;                                          // 16 local pivot positions of the current panel
-    int* info_sh = lp + 16;
-
-    T* Lg = p.ws + (long long)blockIdx.x * p.ws_stride;          // [nb][R original rows][16]: negated multipliers
-    T* Ug = Lg + (long long)nb * R * 16;                         // [nb][nb][256]: U[b, k] in A-fragment order
-    T* LIg = Ug + (long long)nb * nb * 256;                      // [nb][256]: inverse of the unit-lower diagonal blocks (A order)
-    T* UIg = LIg + (long long)nb * 256;                          // [nb][256]: inverse of the upper diagonal blocks (A order)
-    T* ringw = ring + (size_t)warp * NSTAGE * 128;
-    const bool hasA0 = p.A0 != nullptr, hasA1 = p.A1 != nullptr, hasA2 = p.A2 != nullptr;
-
-    FragOff fop;                                                 // fragment offsets in the swizzled panel (leading dimension 16)
-    {
-        const int sg = swz(g);
-        fop.g = g; fop.a0 = t ^ sg; fop.a1 = (4 + t) ^ sg; fop.c0 = (2 * t) ^ sg; fop.c1 = (2 * t + 1) ^ sg;
-        fop.b0 = t * 16 + (g ^ swz(t)); fop.b1 = (4 + t) * 16 + (g ^ swz(4 + t));
-    }
-
-    for (long long pt = blockIdx.x; pt < p.F; pt += gridDim.x) {
-        const double c0 = p.c0[pt], c1 = p.c1[pt], c2 = p.c2[pt], cb = p.cb[pt];
-        for (int i = tid; i < R; i += NT) perm[i] = i;
-        if (tid == 0) *info_sh = 0;
-        __syncthreads();
-
-        T C[RBW][2][2][2];                                       // [owned block][row tile][column tile][e]: rows 8 rb8 + g, columns 8 ct + 2 t + e
-
-        // (U_b | y_b) = D^-1-like product of a finished block with an inverted 16 x 16 diagonal block (A operand, global),
-        // published to BC slot b in B-fragment order; the C registers of the block are replaced by the result.
-        auto convert = [&](T (&Cb)[2][2][2], const T* inv, const bool upper, const int nct, T* slot, T* ublk) {
-#pragma unroll
-            for (int rb8 = 0; rb8 < 2; ++rb8)
-#pragma unroll
-                for (int ct = 0; ct < 2; ++ct)
-#pragma unroll
-                    for (int e = 0; e < 2; ++e) xch[bfrag_off(8 * rb8 + g, 8 * ct + 2 * t + e)] = Cb[rb8][ct][e];
-            __syncwarp();
-            T D[2][2][2];
-#pragma unroll
-            for (int rb8 = 0; rb8 < 2; ++rb8)
-#pragma unroll
-                for (int ct = 0; ct < 2; ++ct) { D[rb8][ct][0] = Num<T>::zero(); D[rb8][ct][1] = Num<T>::zero(); }
-#pragma unroll
-            for (int rb8 = 0; rb8 < 2; ++rb8) {
-#pragma unroll
-                for (int kk = 0; kk < 4; ++kk) {
-                    const bool need = upper ? (rb8 == 0 || kk >= 2) : (rb8 == 1 || kk < 2);   // triangular: skip the zero 8 x 8 block
-                    if (need) {
-                        const T a = inv[((rb8 * 4 + kk) << 5) + lane];
-#pragma unroll
-                        for (int ct = 0; ct < 2; ++ct)
-                            if (ct < nct) Num<T>::mma(D[rb8][ct][0], D[rb8][ct][1], a, xch[((kk * 2 + ct) << 5) + lane]);
-                    }
-                }
-            }
-#pragma unroll
-            for (int rb8 = 0; rb8 < 2; ++rb8)
-#pragma unroll
-                for (int ct = 0; ct < 2; ++ct) {
-#pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        slot[bfrag_off(8 * rb8 + g, 8 * ct + 2 * t + e)] = D[rb8][ct][e];
-                        Cb[rb8][ct][e] = D[rb8][ct][e];
-                    }
-                    if (ublk) {                                  // U[b, j] for the back substitution, A-fragment order (two consecutive elements)
-                        T* dst = ublk + afrag_off(8 * rb8 + g, 8 * ct + 2 * t);
-                        dst[0] = D[rb8][ct][0]; dst[1] = D[rb8][ct][1];
-                    }
-                }
-        };
-
-        for (int j = 0; j <= nb; ++j) {
-            const bool isrhs = (j == nb);
-            const int jj = isrhs ? nb : j;                       // finished panels to the left
-            const int nct = isrhs ? mct : 2;
-
-            // ---- LOAD: block column j of [A(t) | cb Br], rows in pivoted order, into the accumulator registers ----
-#pragma unroll
-            for (int bi = 0; bi < RBW; ++bi) {
-                const int b = warp + bi * NW;
-#pragma unroll
-                for (int rb8 = 0; rb8 < 2; ++rb8) {
-                    const int o = (b < nb) ? perm[16 * b + 8 * rb8 + g] : 0;
-#pragma unroll
-                    for (int ct = 0; ct < 2; ++ct)
-#pragma unroll
-                        for (int e = 0; e < 2; ++e) {
-                            T v = Num<T>::zero();
-                            const int cl = 8 * ct + 2 * t + e;
-                            if (b < nb) {
-                                if (!isrhs) {
-                                    const int cg = 16 * j + cl;
-                                    if (o < r && cg < r) {
-                                        const long long off = (long long)o * p.lda + cg;
-                                        if (hasA0) v = Num<T>::scale(c0, __ldg(p.A0 + off));
-                                        if (hasA1) Num<T>::axpy(v, c1, __ldg(p.A1 + off));
-                                        if (hasA2) Num<T>::axpy(v, c2, __ldg(p.A2 + off));
-                                    } else if (o == cg) v = Num<T>::one();      // identity on the padded diagonal
-                                } else if (o < r && cl < m) v = Num<T>::scale(cb, __ldg(p.Br + (long long)o * p.ldb + cl));
-                            }
-                            C[bi][rb8][ct][e] = v;
-                        }
-                }
-            }
-
-            // ---- CHAIN: C_b += (-L[b, k]) U[k, j] for k < jj; U[k+1, j] published after step k ----
-            if (jj > 0) {
-                // unit = (step k, owned block bi, row tile rb8); the producer iterator runs NSTAGE - 1 units ahead
-                int pk = 0, pbi = 0, prb = 0, ck = 0, cbi = 0, crb = 0;
-                auto seek = [&](int& k, int& bi) {               // first unit at or after (k, bi): owned block b > k
-                    while (k < jj) {
-                        while (bi < RBW) {
-                            const int b = warp + bi * NW;
-                            if (b >= nb) { bi = RBW; break; }
-                            if (b > k) return;
-                            ++bi;
-                        }
-                        ++k; bi = 0;
-                    }
-                };
-                auto next = [&](int& k, int& bi, int& rb) {
-                    if (rb == 0) { rb = 1; return; }
-                    rb = 0; ++bi;
-                    seek(k, bi);
-                };
-                auto issue = [&](const int k, const int bi, const int rb, const int stage) {
-                    const int b = warp + bi * NW;
-                    const int o = perm[16 * b + 8 * rb + g];
-                    const T* src = Lg + ((long long)k * R + o) * 16 + t;
-                    T* dst = ringw + stage * 128 + lane;
-#pragma unroll
-                    for (int kk = 0; kk < 4; ++kk) Num<T>::cp_async(dst + 32 * kk, src + 4 * kk);
-                };
-                seek(pk, pbi);
-                seek(ck, cbi);
-                int pstage = 0, cstage = 0;
-#pragma unroll
-                for (int s = 0; s < NSTAGE - 1; ++s) {
-                    if (pk < jj) { issue(pk, pbi, prb, pstage); next(pk, pbi, prb); }
-                    cpa_commit();
-                    pstage = (pstage + 1 == NSTAGE) ? 0 : pstage + 1;
-                }
-                if (warp == 0) convert(C[0], LIg, false, nct, BC, isrhs ? nullptr : Ug + (long long)j * 256);   // block 0: U[0, j]
-                __syncthreads();
-                for (int k = 0; k < jj; ++k) {
-                    const T* Uk = BC + k * 256;                  // U[k, j], B-fragment order
-                    T bfr[CACHE_B ? 4 : 1][2];
-                    if (CACHE_B) {
-#pragma unroll
-                        for (int kk = 0; kk < 4; ++kk)
-#pragma unroll
-                            for (int ct = 0; ct < 2; ++ct) bfr[CACHE_B ? kk : 0][ct] = Uk[((kk * 2 + ct) << 5) + lane];
-                    }
-                    while (ck == k) {
-                        if (pk < jj) { issue(pk, pbi, prb, pstage); next(pk, pbi, prb); }
-                        cpa_commit();
-                        pstage = (pstage + 1 == NSTAGE) ? 0 : pstage + 1;
-                        cpa_wait<NSTAGE - 1>();
-                        const T* af = ringw + cstage * 128 + lane;
-#pragma unroll
-                        for (int bi = 0; bi < RBW; ++bi) {       // static register indexing of C
-                            if (bi == cbi) {
-#pragma unroll
-                                for (int rb = 0; rb < 2; ++rb) {
-                                    if (rb == crb) {
-#pragma unroll
-                                        for (int kk = 0; kk < 4; ++kk) {
-                                            const T a = af[32 * kk];
-#pragma unroll
-                                            for (int ct = 0; ct < 2; ++ct)
-                                                if (ct < nct) {
-                                                    const T bq = CACHE_B ? bfr[CACHE_B ? kk : 0][ct] : Uk[((kk * 2 + ct) << 5) + lane];
-                                                    Num<T>::mma(C[bi][rb][ct][0], C[bi][rb][ct][1], a, bq);
-                                                }
-                                        }
-                                    }
-                                }
-                                // block row k + 1 is final after step k: publish U[k + 1, j]
-                                if (crb == 1 && warp + bi * NW == k + 1 && k + 1 < jj)
-                                    convert(C[bi], LIg + (long long)(k + 1) * 256, false, nct, BC + (k + 1) * 256,
-                                            isrhs ? nullptr : Ug + ((long long)(k + 1) * nb + j) * 256);
-                            }
-                        }
-                        cstage = (cstage + 1 == NSTAGE) ? 0 : cstage + 1;
-                        next(ck, cbi, crb);
-                    }
-                    __syncthreads();
-                }
-                cpa_wait<0>();
-            }
-            if (isrhs) break;
-
-            // ---- PANEL: rows at positions >= 16 j -> shared memory (swizzled), LU with partial pivoting ----
-            T* PB = BC + (size_t)j * 256;
-            const int rows = R - 16 * j;
-#pragma unroll
-            for (int bi = 0; bi < RBW; ++bi) {
-                const int b = warp + bi * NW;
-                if (b >= j && b < nb) {
-#pragma unroll
-                    for (int rb8 = 0; rb8 < 2; ++rb8)
-#pragma unroll
-                        for (int ct = 0; ct < 2; ++ct)
-#pragma unroll
-                            for (int e = 0; e < 2; ++e)
-                                PB[mphys(16 * (b - j) + 8 * rb8 + g, 8 * ct + 2 * t + e, 16)] = C[bi][rb8][ct][e];
-                }
-            }
-            __syncthreads();
-#pragma unroll 1
-            for (int ip = 0; ip < 2; ++ip) {
-                const int row0 = 8 * ip;
-                int* pvl = lp + row0;
-                if (SL > 1 && rows - row0 > NT) panel_factor_t<T, SL, NW>(PB, 16, rows, row0, tid, candk, candrow, pvl, info_sh, 16 * j);
-                else panel_factor_t<T, 1, NW>(PB, 16, rows, row0, tid, candk, candrow, pvl, info_sh, 16 * j);
-                __syncthreads();
-                if (tid < row0) {                                // the exchanges also apply to the multipliers of the first inner panel
-                    const int c = tid, cbase = c & ~7, cin = c & 7;
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        const int P = pvl[q], Tg = row0 + q;
-                        if (P != Tg) {
-                            T* x = PB + Tg * 16 + cbase + (cin ^ swz(q));
-                            T* y = PB + P * 16 + cbase + (cin ^ swz(P & 7));
-                            const T tmp = *x; *x = *y; *y = tmp;
-                        }
-                    }
-                }
-                if (ip == 0) {
-                    if (tid < 8) stepb_column_t<T>(PB, 16, 0, 8 + tid, pvl);
-                    __syncthreads();
-                    // rows 8 .. rows-1, columns 8..15 += (-L21) U12 : one 8 x 8 tile per row tile, dealt to the warps
-                    const int ntiles = rows / 8 - 1;
-                    const T b0 = PB[8 + fop.b0], b1 = PB[8 + fop.b1];
-                    for (int ti = warp; ti < ntiles; ti += NW) {
-                        T* rowp = PB + (8 * (1 + ti) + g) * 16;
-                        const T a0 = rowp[fop.a0], a1 = rowp[fop.a1];
-                        T v0 = rowp[8 + fop.c0], v1 = rowp[8 + fop.c1];
-                        Num<T>::mma(v0, v1, a0, b0);
-                        Num<T>::mma(v0, v1, a1, b1);
-                        rowp[8 + fop.c0] = v0; rowp[8 + fop.c1] = v1;
-                    }
-                    __syncthreads();
-                }
-            }
-            __syncthreads();
-            // ---- STORE: perm, multipliers (by original row), inverses of the diagonal blocks ----
-            if (tid == 0) {
-                for (int c = 0; c < 16; ++c) { const int P = 16 * j + lp[c]; const int tmp = perm[16 * j + c]; perm[16 * j + c] = perm[P]; perm[P] = tmp; }
-            }
-            __syncthreads();
-            for (int e = tid; e < (rows - 16) * 16; e += NT) {
-                const int lr = 16 + (e >> 4), c = e & 15;
-                const int o = perm[16 * j + lr];
-                Lg[((long long)j * R + o) * 16 + c] = PB[mphys(lr, c, 16)];
-            }
-            if (tid < 32) {
-                const int c = tid & 15;
-                T x[16];
-                if (tid < 16) {                                  // column c of (I - S)^-1, S = stored (negated) multipliers of L11
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        T acc = (i == c) ? Num<T>::one() : Num<T>::zero();
-#pragma unroll
-                        for (int k = 0; k < i; ++k) Num<T>::fma_(acc, PB[mphys(i, k, 16)], x[k]);
-                        x[i] = acc;
-                    }
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) LIg[(long long)j * 256 + afrag_off(i, c)] = x[i];
-                } else {                                         // column c of U11^-1 (reciprocal pivots on the stored diagonal)
-#pragma unroll
-                    for (int i = 15; i >= 0; --i) {
-                        T acc = (i == c) ? Num<T>::one() : Num<T>::zero();
-#pragma unroll
-                        for (int k = i + 1; k < 16; ++k) Num<T>::fma_(acc, Num<T>::neg(PB[mphys(i, k, 16)]), x[k]);
-                        x[i] = Num<T>::mul(acc, PB[mphys(i, i, 16)]);
-                    }
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) UIg[(long long)j * 256 + afrag_off(i, c)] = x[i];
-                }
-            }
-            __syncthreads();
-        }
-
-        // ---- back substitution: x_k = U_kk^-1 (y_k - sum_{k' > k} U[k, k'] x_k'), blocks from the last to the first ----
-        // y_b sits in the C registers of the warp that owns block b (left there by the right-hand-side block column).
-        for (int k = nb - 1; k >= 0; --k) {
-#pragma unroll
-            for (int bi = 0; bi < RBW; ++bi)
-                if (warp + bi * NW == k) convert(C[bi], UIg + (long long)k * 256, true, mct, BC + k * 256, nullptr);
-            __syncthreads();
-            const T* Xk = BC + k * 256;
-#pragma unroll
-            for (int bi = 0; bi < RBW; ++bi) {
-                const int b = warp + bi * NW;
-                if (b < k) {
-                    const T* ub = Ug + ((long long)b * nb + k) * 256 + lane;
-#pragma unroll
-                    for (int rb8 = 0; rb8 < 2; ++rb8)
-#pragma unroll
-                        for (int kk = 0; kk < 4; ++kk) {
-                            const T a = Num<T>::neg(ub[(rb8 * 4 + kk) << 5]);
-#pragma unroll
-                            for (int ct = 0; ct < 2; ++ct)
-                                if (ct < mct) Num<T>::mma(C[bi][rb8][ct][0], C[bi][rb8][ct][1], a, Xk[((kk * 2 + ct) << 5) + lane]);
-                        }
-                }
-            }
-        }
-        __syncthreads();
-        // ---- outputs: x (position k = original unknown k: there is no column pivoting), Z = j zs x^T (cb Br) -> S ----
-        auto xs = [&](const int i, const int c) -> T { return BC[(i >> 4) * 256 + bfrag_off(i & 15, c)]; };
-        if (p.X) for (int e = tid; e < r * m; e += NT) { const int i = e / m, c = e - i * m; p.X[pt * (long long)r * m + e] = xs(i, c); }
-        if (p.info && tid == 0) p.info[pt] = *info_sh;
-        if (p.S) {
-            for (int e = warp; e < m * m; e += NW) {
-                const int a = e / m, b = e - a * m;
-                T acc = Num<T>::zero();
-                for (int k = lane; k < r; k += 32) Num<T>::fma_(acc, xs(k, a), Num<T>::scale(cb, __ldg(p.Br + (long long)k * p.ldb + b)));
-                acc = warp_sum(acc);
-                if (lane == 0) p.S[pt * (long long)m * m + e] = Num<T>::jz(p.zs[pt], acc);
-            }
-        }
-        __syncthreads();
-    }
-}
-
-
 // ======================================================================================================================
-// Version 2 of the kernel body.  Same algorithm and storage as above, restructured after the first ncu capture
-// (profiles/r02_sweep_left_v1_ncu.md: 1.23 M warp instructions per point of which 8 % DMMA; 24 % of the stall samples at the
-// per-step CTA barrier of the chain):
+// The kernel, second version of the body (the first one -- block ownership, a CTA barrier per chain step, the product with
+// the inverted diagonal block inside every chain link -- is in the history; its ncu capture, profiles/r02_sweep_left_v1_ncu.md,
+// showed 1.23 M warp instructions per point of which 8 % DMMA and 24 % of the stall samples at the per-step barrier):
 //   * accumulators live in the register form DMMA wants (re[2] / im[2] quads) -- no register shuffles around the MMAs;
 //   * ownership by 8-row TILE, cyclic over the warps, and a static (unrolled) unit loop with a closed-form prefetch
 //     iterator instead of the dynamic one;
@@ -648,6 +311,82 @@ template <> struct Acc<cplx> {
     __device__ __forceinline__ cplx get(int e) const { return cmake(re[e], im[e]); }
     __device__ __forceinline__ void set(int e, cplx x) { re[e] = x.x; im[e] = x.y; }
 };
+
+// Inverse of a 16 x 16 triangular diagonal block of the factored panel (rows 0..15 of PB, swizzled, leading dimension 16), by ONE
+// warp: the two 8 x 8 diagonal blocks by substitution (one column per lane, 7 dependent steps instead of 15), the off-diagonal
+// block as two 8 x 8 x 8 DMMA products.  LOWER: L = I - S, S = the stored (negated) multipliers, inv = [[A^-1, 0], [C^-1 S_B A^-1, C^-1]];
+// UPPER: U with the reciprocal pivots stored on the diagonal, inv = [[A^-1, -A^-1 B C^-1], [0, C^-1]].  The result goes to `outg`
+// (global) and, if given, `outs` (shared) in A-fragment order; scr = 256 elements of shared scratch owned by the warp.
+template <typename T, bool UPPER>
+__device__ __forceinline__ void tri_inverse16(const T* PB, T* scr, T* outg, T* outs, const int lane) {
+    T* D0 = scr;                                                  // inverse of the leading 8 x 8 block, row-major
+    T* D1 = scr + 64;                                             // inverse of the trailing 8 x 8 block
+    T* T1 = scr + 128;                                            // intermediate product
+    T* W = scr + 192;                                             // off-diagonal block of the inverse
+    const int g = lane >> 2, t = lane & 3;
+    if (lane < 16) {
+        const int blk = lane >> 3, c = lane & 7, o = 8 * blk;
+        T x[8];
+        if (!UPPER) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                T acc = (i == c) ? Num<T>::one() : Num<T>::zero();
+#pragma unroll
+                for (int k = 0; k < i; ++k) Num<T>::fma_(acc, PB[mphys(o + i, o + k, 16)], x[k]);
+                x[i] = acc;
+            }
+        } else {
+#pragma unroll
+            for (int i = 7; i >= 0; --i) {
+                T acc = (i == c) ? Num<T>::one() : Num<T>::zero();
+#pragma unroll
+                for (int k = i + 1; k < 8; ++k) Num<T>::fma_(acc, Num<T>::neg(PB[mphys(o + i, o + k, 16)]), x[k]);
+                x[i] = Num<T>::mul(acc, PB[mphys(o + i, o + i, 16)]);
+            }
+        }
+        T* D = blk ? D1 : D0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) D[i * 8 + c] = x[i];
+    }
+    __syncwarp();
+    {
+        // first product: LOWER  T1 = S_B A^-1 (S_B = rows 8..15, columns 0..7);  UPPER  T1 = B C^-1 (B = rows 0..7, columns 8..15)
+        const T* Dr = UPPER ? D1 : D0;
+        Acc<T> acc; acc.zero();
+#pragma unroll
+        for (int kk = 0; kk < 2; ++kk) {
+            const T a = UPPER ? PB[mphys(g, 8 + 4 * kk + t, 16)] : PB[mphys(8 + g, 4 * kk + t, 16)];
+            const T b = Dr[(4 * kk + t) * 8 + g];
+            acc.mma1(a, b); acc.mma2(a, b);
+        }
+        T1[g * 8 + 2 * t] = acc.get(0); T1[g * 8 + 2 * t + 1] = acc.get(1);
+    }
+    __syncwarp();
+    {
+        // second product: LOWER  W = C^-1 T1;  UPPER  W = -(A^-1 T1)
+        const T* Dl = UPPER ? D0 : D1;
+        Acc<T> acc; acc.zero();
+#pragma unroll
+        for (int kk = 0; kk < 2; ++kk) {
+            const T a = Dl[g * 8 + 4 * kk + t];
+            const T b = T1[(4 * kk + t) * 8 + g];
+            acc.mma1(a, b); acc.mma2(a, b);
+        }
+        W[g * 8 + 2 * t] = UPPER ? Num<T>::neg(acc.get(0)) : acc.get(0);
+        W[g * 8 + 2 * t + 1] = UPPER ? Num<T>::neg(acc.get(1)) : acc.get(1);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const int e = lane + 32 * q, i = e >> 4, c = e & 15;
+        T v;
+        if (i < 8) v = (c < 8) ? D0[i * 8 + c] : (UPPER ? W[i * 8 + c - 8] : Num<T>::zero());
+        else v = (c < 8) ? (UPPER ? Num<T>::zero() : W[(i - 8) * 8 + c]) : D1[(i - 8) * 8 + c - 8];
+        outg[afrag_off(i, c)] = v;
+        if (outs) outs[afrag_off(i, c)] = v;
+    }
+    __syncwarp();
+}
 
 // NW warps; warp w owns the 8-row tiles w, w + NW, ... (TPW of them at most); MINB CTAs per SM; NSTAGE = FIFO depth.
 template <typename T, int NW, int TPW, int MINB, int NSTAGE>
@@ -1037,28 +776,540 @@ __global__ void __launch_bounds__(NW * 32, MINB) sweep_left2_kernel(SweepParamsL
 }
 
 
+// ======================================================================================================================
+// Look-ahead version.  The ncu capture of the version above (profiles/r02_sweep_left_v2_ncu.md) shows the DMMA pipe 45 % busy with
+// two CTAs per SM: a block column is LOAD -> chain (latency bound: 2 j links) -> panel (16 column steps, a CTA barrier each) -> STORE,
+// strictly one after the other, and the tensor pipe idles through the panel.  But block column j + 1 only needs panel j for its rows
+// at positions >= 16 j: the rows of the finished blocks b < j -- the whole latency-bound chain U[0 .. j-1, j+1] -- depend on panels
+// < j only.  So each step of the outer loop now runs
+//   phase A   warps 0 .. NW/2-1: panel j + STORE (named barrier, half of the CTA)
+//             warps NW/2 .. NW-1: the chain of column j + 1 over the finished blocks b < j, tile by tile (tile t = rows 8t..8t+7 of the
+//             pivoted order): L_bb^-1 A[b, j+1] at load time, the b updates as the U blocks above are announced, publication;
+//   phase B   all warps: the rows that needed panel j -- the two tiles of block j (their U rows are the last link) and the rows below,
+//             which take all j + 1 updates with U already in shared memory, and go to shared memory as panel j + 1.
+// ======================================================================================================================
+template <typename T, int NW, int TPW, int MINB, int NSTAGE>
+__global__ void __launch_bounds__(NW * 32, MINB) sweep_left3_kernel(SweepParamsL<T> p, int R) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int NT = NW * 32;
+    constexpr int NWP = NW / 2, NTP = NWP * 32;                  // panel warps / threads
+    constexpr int NWE = NW - NWP;                                // warps that run ahead during the panel
+    constexpr int SLP = (TPW + 1) / 2;                           // rows per panel thread (R <= 8 NW TPW, NTP threads)
+    constexpr int RBW = (TPW + 1) / 2;                           // 16-row blocks per warp in the back substitution
+    const int r = p.r, m = p.m, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, tl = lane & 3;
+    const int nb = R >> 4, ntiles = R >> 3;
+    const int mct = (m + 7) >> 3;
+
+    T* BC = reinterpret_cast<T*>(smem_raw);                      // R x 16: U blocks (fragment order) | panel rows (swizzled)
+    T* ring = BC + (size_t)R * 16;                               // NW x NSTAGE x 128: per-lane FIFO of L fragments
+    T* xch = ring + (size_t)NW * NSTAGE * 128;                   // 256: inverse of the current unit-lower block (A order) / exchange
+    T* candrow = xch + 256;                                      // 2 x NW x 8
+    CandKeyL* candk = reinterpret_cast<CandKeyL*>(candrow + 2 * NW * 8);   // 2 x NW
+    int* perm = reinterpret_cast<int*>(candk + 2 * NW);          // R: position -> original row
+    int* uflag = perm + R;                                       // R / 8: epoch at which tile t of the current block column was published
+    int* lp = uflag + (R >> 3);                                  // 16 local pivot positions of the current panel
+    int* info_sh = lp + 16;
+
+    T* Lg = p.ws + (long long)blockIdx.x * p.ws_stride;          // [nb][R original rows][16]: negated multipliers (L~ for finished blocks)
+    T* Ug = Lg + (long long)nb * R * 16;                         // [nb][nb][256]: U[b, k] in A-fragment order
+    T* LIg = Ug + (long long)nb * nb * 256;                      // [nb][256]: inverse of the unit-lower diagonal blocks (A order)
+    T* UIg = LIg + (long long)nb * 256;                          // [nb][256]: inverse of the upper diagonal blocks (A order)
+    T* ringw = ring + (size_t)warp * NSTAGE * 128;
+    const bool hasA0 = p.A0 != nullptr, hasA1 = p.A1 != nullptr, hasA2 = p.A2 != nullptr;
+
+    FragOff fop;
+    {
+        const int sg = swz(g);
+        fop.g = g; fop.a0 = tl ^ sg; fop.a1 = (4 + tl) ^ sg; fop.c0 = (2 * tl) ^ sg; fop.c1 = (2 * tl + 1) ^ sg;
+        fop.b0 = tl * 16 + (g ^ swz(tl)); fop.b1 = (4 + tl) * 16 + (g ^ swz(4 + tl));
+    }
+    for (int i = tid; i < (R >> 3); i += NT) uflag[i] = 0;
+    int epoch0 = 0;
+    // phase timers (clock64 sums of CTA 0): 0 point, 1 panel, 2 store + inverses, 3 L~, 4 early chain, 5 phase A (CTA barrier to CTA barrier),
+    // 6 phase B, 7 back substitution, 8 column-0 load
+    unsigned long long* tim = (p.timing && blockIdx.x == 0) ? p.timing : nullptr;
+    auto tick = [&]() -> long long { return tim ? clock64() : 0; };
+    auto tock = [&](const int slot, const long long t0, const int who) { if (tim && tid == who) tim[slot] += (unsigned long long)(clock64() - t0); };                                              // epoch of column c of the current point = epoch0 + c + 1
+
+    for (long long pt = blockIdx.x; pt < p.F; pt += gridDim.x) {
+        const double c0 = p.c0[pt], c1 = p.c1[pt], c2 = p.c2[pt], cb = p.cb[pt];
+        const long long t_pt = tick();
+        for (int i = tid; i < R; i += NT) perm[i] = i;
+        if (tid == 0) *info_sh = 0;
+        __syncthreads();
+
+        // element (original row o, local column cl) of block column jc of [A(t) | cb Br] (jc == nb: the right-hand sides)
+        auto elem = [&](const int jc, const int o, const int cl) -> T {
+            if (jc == nb) {
+                const bool in = (o < r) & (cl < m);
+                const T x = __ldg(p.Br + (in ? (long long)o * p.ldb + cl : 0));
+                return in ? Num<T>::scale(cb, x) : Num<T>::zero();
+            }
+            const int cg = 16 * jc + cl;
+            const bool in = (o < r) & (cg < r);
+            const long long off = in ? (long long)o * p.lda + cg : 0;
+            T v = Num<T>::zero();
+            if (hasA0) v = Num<T>::scale(c0, __ldg(p.A0 + off));
+            if (hasA1) Num<T>::axpy(v, c1, __ldg(p.A1 + off));
+            if (hasA2) Num<T>::axpy(v, c2, __ldg(p.A2 + off));
+            return in ? v : ((o == cg) ? Num<T>::one() : Num<T>::zero());
+        };
+        // rows of a finished block b at load time: Ct = (L_bb^-1)[rows 8h .. 8h+7] A[b, jc]  (lower triangular inverse, A operand)
+        auto init_u = [&](Acc<T> (&Ct)[2], const int t, const int jc, const int nct) {
+            const int b = t >> 1, h = t & 1;
+            const T* li = LIg + (long long)b * 256 + ((h * 4) << 5) + lane;
+            Ct[0].zero(); Ct[1].zero();
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+                if (kk < 2 || h == 1) {
+                    const T a = li[kk << 5];
+                    const int ok = perm[16 * b + 4 * kk + tl];
+                    const T b0 = elem(jc, ok, g), b1 = elem(jc, ok, 8 + g);
+                    Ct[0].mma1(a, b0); if (nct > 1) Ct[1].mma1(a, b1);
+                    Ct[0].mma2(a, b0); if (nct > 1) Ct[1].mma2(a, b1);
+                }
+            }
+        };
+        // U rows of a finished tile -> shared slot (B-fragment order), global (A-fragment order, for the back substitution), flag
+        auto publish = [&](const Acc<T> (&Ct)[2], const int t, const int jc, const int ep) {
+            const int b = t >> 1, h = t & 1;
+            T* slot = BC + b * 256;
+#pragma unroll
+            for (int ct = 0; ct < 2; ++ct)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) slot[bfrag_off(8 * h + g, 8 * ct + 2 * tl + e)] = Ct[ct].get(e);
+            if (jc < nb) {
+                T* ub = Ug + ((long long)b * nb + jc) * 256;
+#pragma unroll
+                for (int ct = 0; ct < 2; ++ct) {
+                    T* dst = ub + afrag_off(8 * h + g, 8 * ct + 2 * tl);
+                    dst[0] = Ct[ct].get(0); dst[1] = Ct[ct].get(1);
+                }
+            }
+            __syncwarp();
+            __threadfence_block();
+            if (lane == 0) *reinterpret_cast<volatile int*>(uflag + t) = ep;
+        };
+        auto wait_u = [&](const int k, const int ep) {
+            volatile int* f = uflag + 2 * k;
+            while (f[0] != ep || f[1] != ep) { __nanosleep(20); }
+            __threadfence_block();
+        };
+        // one 8 x 16 x 16 tile update: A fragments from a FIFO stage, B fragments = U[k, .] in its shared slot
+        auto unit = [&](Acc<T> (&Ct)[2], const T* af, const T* Uk, const int nct) {
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+                const T a = af[32 * kk];
+                const T b0 = Uk[(kk * 2) << 5], b1 = Uk[(kk * 2 + 1) << 5];
+                Ct[0].mma1(a, b0); if (nct > 1) Ct[1].mma1(a, b1);
+                Ct[0].mma2(a, b0); if (nct > 1) Ct[1].mma2(a, b1);
+            }
+        };
+
+        Acc<T> C[TPW][2];
+
+        // ---- block column 0: every row is below the (empty) factored part: plain load, straight to the panel buffer ----
+#pragma unroll
+        for (int i = 0; i < TPW; ++i) {
+            const int t = warp + NW * i;
+            if (t < ntiles) {
+                const int o = perm[8 * t + g];
+#pragma unroll
+                for (int ct = 0; ct < 2; ++ct)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) BC[mphys(8 * t + g, 8 * ct + 2 * tl + e, 16)] = elem(0, o, 8 * ct + 2 * tl + e);
+            }
+        }
+        __syncthreads();
+        tock(8, t_pt, 0);
+
+        for (int j = 0; j < nb; ++j) {
+            const long long t_a = tick();
+            const int jn = j + 1;                                // the column whose chain overlaps with panel j (jn == nb: right-hand sides)
+            const int nctn = (jn == nb) ? mct : 2;
+            const int epn = epoch0 + jn + 1;
+            // ================================================ phase A ================================================
+            if (warp < NWP) {
+                // ---- panel j (positions >= 16 j, in shared memory) by the panel warps, named barrier 1 ----
+                T* PB = BC + (size_t)j * 256;
+                const int rows = R - 16 * j;
+#pragma unroll 1
+                for (int ip = 0; ip < 2; ++ip) {
+                    const int row0 = 8 * ip;
+                    int* pvl = lp + row0;
+                    if (SLP > 1 && rows - row0 > NTP) panel_factor_t<T, SLP, NWP, NTP>(PB, 16, rows, row0, tid, candk, candrow, pvl, info_sh, 16 * j);
+                    else panel_factor_t<T, 1, NWP, NTP>(PB, 16, rows, row0, tid, candk, candrow, pvl, info_sh, 16 * j);
+                    csync<NTP>();
+                    if (tid < row0) {                            // the exchanges also apply to the multipliers of the first inner panel
+                        const int c = tid, cbase = c & ~7, cin = c & 7;
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            const int P = pvl[q], Tg = row0 + q;
+                            if (P != Tg) {
+                                T* x = PB + Tg * 16 + cbase + (cin ^ swz(q));
+                                T* y = PB + P * 16 + cbase + (cin ^ swz(P & 7));
+                                const T tmp = *x; *x = *y; *y = tmp;
+                            }
+                        }
+                    }
+                    if (ip == 0) {
+                        if (tid < 8) stepb_column_t<T>(PB, 16, 0, 8 + tid, pvl);
+                        csync<NTP>();
+                        const int ntl = rows / 8 - 1;
+                        const T b0 = PB[8 + fop.b0], b1 = PB[8 + fop.b1];
+                        for (int ti = warp; ti < ntl; ti += NWP) {
+                            T* rowp = PB + (8 * (1 + ti) + g) * 16;
+                            const T a0 = rowp[fop.a0], a1 = rowp[fop.a1];
+                            Acc<T> v;
+                            v.set(0, rowp[8 + fop.c0]); v.set(1, rowp[8 + fop.c1]);
+                            v.mma1(a0, b0); v.mma2(a0, b0);
+                            v.mma1(a1, b1); v.mma2(a1, b1);
+                            rowp[8 + fop.c0] = v.get(0); rowp[8 + fop.c1] = v.get(1);
+                        }
+                        csync<NTP>();
+                    }
+                }
+                csync<NTP>();
+                tock(1, t_a, 0);
+                const long long t_s = tick();
+                // ---- STORE: perm, multipliers (by original row), inverses of the diagonal blocks, L~ ----
+                // warp 0: inverse of the unit-lower diagonal block (kept in shared memory for L~ below); warp 1: inverse of the upper one
+                // (each uses its own idle FIFO stages as scratch); meanwhile one lane of the last panel warp applies the 16 exchanges to perm[]
+                if (warp == 0) tri_inverse16<T, false>(PB, ringw, LIg + (long long)j * 256, xch, lane);
+                else if (warp == 1) tri_inverse16<T, true>(PB, ringw, UIg + (long long)j * 256, nullptr, lane);
+                if (tid == (NWP > 2 ? 64 : 32)) {                 // first lane of warp 2 (of warp 1, after its inverse, when there are two panel warps)
+                    int lpr[16];
+#pragma unroll
+                    for (int c = 0; c < 16; ++c) lpr[c] = lp[c];
+#pragma unroll
+                    for (int c = 0; c < 16; ++c) { const int P = 16 * j + lpr[c]; const int tmp = perm[16 * j + c]; perm[16 * j + c] = perm[P]; perm[P] = tmp; }
+                }
+                csync<NTP>();
+                for (int e = tid; e < (rows - 16) * 16; e += NTP) {
+                    const int lr = 16 + (e >> 4), c = e & 15;
+                    const int o = perm[16 * j + lr];
+                    Lg[((long long)j * R + o) * 16 + c] = PB[mphys(lr, c, 16)];
+                }
+                tock(2, t_s, 0);
+                const long long t_l = tick();
+                for (int k = warp; k < j; k += NWP) {            // L~: rows of block j in the earlier panels, times L_jj^-1, in place
+                    T* Lk = Lg + (long long)k * R * 16;
+                    T bq[4][2];
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk) {
+                        const T* rowp = Lk + (long long)perm[16 * j + 4 * kk + tl] * 16;
+                        bq[kk][0] = rowp[g]; bq[kk][1] = rowp[8 + g];
+                    }
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        Acc<T> d0, d1;
+                        d0.zero(); d1.zero();
+#pragma unroll
+                        for (int kk = 0; kk < 4; ++kk) {
+                            if (kk < 2 || h == 1) {
+                                const T a = xch[((h * 4 + kk) << 5) + lane];
+                                d0.mma1(a, bq[kk][0]); d1.mma1(a, bq[kk][1]);
+                                d0.mma2(a, bq[kk][0]); d1.mma2(a, bq[kk][1]);
+                            }
+                        }
+                        T* rowp = Lk + (long long)perm[16 * j + 8 * h + g] * 16 + 2 * tl;
+                        rowp[0] = d0.get(0); rowp[1] = d0.get(1);
+                        rowp[8] = d1.get(0); rowp[9] = d1.get(1);
+                    }
+                }
+                tock(3, t_l, 0);
+                if (warp >= 1 && warp <= 3) tock(12 + warp, t_a, 32 * warp);     // end of phase A work of the other panel warps
+            } else if (j > 0) {
+                // ---- the chain of column jn over the finished blocks b < j, tile by tile (tiles e, e + NWE, ... < 2 j) ----
+                const int ew = warp - NWP;
+                const int nt = 2 * j;
+                // FIFO producer: (tile pt_, step pk) over my tiles in order, k < b(tile)
+                int ptile = ew, pk = 0;
+                auto pnorm = [&]() { while (ptile < nt && pk >= (ptile >> 1)) { ptile += NWE; pk = 0; } };
+                auto issue = [&](const int stage) {
+                    const int o = perm[8 * ptile + g];
+                    const T* src = Lg + ((long long)pk * R + o) * 16 + tl;
+                    T* dst = ringw + stage * 128 + lane;
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk) Num<T>::cp_async(dst + 32 * kk, src + 4 * kk);
+                };
+                pnorm();
+                int pstage = 0, cstage = 0;
+#pragma unroll
+                for (int st = 0; st < NSTAGE - 1; ++st) {
+                    if (ptile < nt) { issue(pstage); ++pk; pnorm(); }
+                    cpa_commit();
+                    pstage = (pstage + 1 == NSTAGE) ? 0 : pstage + 1;
+                }
+#pragma unroll 1
+                for (int t = ew; t < nt; t += NWE) {
+                    init_u(C[0], t, jn, nctn);
+                    const int b = t >> 1;
+#pragma unroll 1
+                    for (int k = 0; k < b; ++k) {
+                        if (ptile < nt) { issue(pstage); ++pk; pnorm(); }
+                        cpa_commit();
+                        pstage = (pstage + 1 == NSTAGE) ? 0 : pstage + 1;
+                        wait_u(k, epn);
+                        cpa_wait<NSTAGE - 1>();
+                        unit(C[0], ringw + cstage * 128 + lane, BC + k * 256 + lane, nctn);
+                        cstage = (cstage + 1 == NSTAGE) ? 0 : cstage + 1;
+                    }
+                    publish(C[0], t, jn, epn);
+                }
+                cpa_wait<0>();
+                tock(4, t_a, NTP);
+                if (warp - NWP >= 1 && warp - NWP <= 3) tock(8 + warp - NWP, t_a, 32 * warp);   // the other early warps
+            }
+            __syncthreads();
+            tock(5, t_a, 0);
+            const long long t_b = tick();
+            // ================================================ phase B ================================================
+            // rows at positions >= 16 j of column jn: tiles t = 2 j + warp + NW i.  Block j (t = 2j, 2j+1) takes j updates and is the
+            // last link of the chain; the rows below take j + 1 updates and become panel jn.
+            {
+                const int nrem = ntiles - 2 * j;
+                const int imax = min(TPW, max(0, (nrem - warp + NW - 1) / NW));
+                int obase[TPW];
+#pragma unroll
+                for (int i = 0; i < TPW; ++i) {
+                    const int t = 2 * j + warp + NW * i;
+                    obase[i] = 0;
+                    C[i][0].zero(); C[i][1].zero();
+                    if (i < imax) {
+                        const int o = perm[8 * t + g];
+                        obase[i] = o * 16 + tl;
+                        if ((t >> 1) == j) init_u(C[i], t, jn, nctn);
+                        else {
+#pragma unroll
+                            for (int ct = 0; ct < 2; ++ct)
+#pragma unroll
+                                for (int e = 0; e < 2; ++e) C[i][ct].set(e, elem(jn, o, 8 * ct + 2 * tl + e));
+                        }
+                    }
+                }
+                // units (k, i): k < j for every owned tile, k == j for the tiles below block j (i >= ilast)
+                const int ilast = (warp < 2) ? 1 : 0;
+                auto ifirst = [&](const int k) { return k < j ? 0 : ilast; };
+                int pk = 0, pi = ifirst(0);
+                auto pnorm = [&]() { while (pk <= j && pi >= imax) { ++pk; pi = ifirst(pk); } };
+                auto issue = [&](const int stage) {
+                    int ob = obase[0];
+#pragma unroll
+                    for (int i = 1; i < TPW; ++i) ob = (pi == i) ? obase[i] : ob;
+                    const T* src = Lg + (long long)pk * R * 16 + ob;
+                    T* dst = ringw + stage * 128 + lane;
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk) Num<T>::cp_async(dst + 32 * kk, src + 4 * kk);
+                };
+                pnorm();
+                int pstage = 0, cstage = 0;
+#pragma unroll
+                for (int st = 0; st < NSTAGE - 1; ++st) {
+                    if (pk <= j) { issue(pstage); ++pi; pnorm(); }
+                    cpa_commit();
+                    pstage = (pstage + 1 == NSTAGE) ? 0 : pstage + 1;
+                }
+                if (j == 0 && warp < 2 && imax > 0) publish(C[0], warp, jn, epn);        // block 0 needs no update
+#pragma unroll 1
+                for (int k = 0; k <= j; ++k) {
+                    const int i0 = ifirst(k);
+                    if (i0 >= imax) continue;
+                    if (k == j) wait_u(j, epn);                  // the last link; the blocks above were announced in phase A
+                    const T* Uk = BC + k * 256 + lane;
+#pragma unroll
+                    for (int i = 0; i < TPW; ++i) {
+                        if (i >= i0 && i < imax) {
+                            if (pk <= j) { issue(pstage); ++pi; pnorm(); }
+                            cpa_commit();
+                            pstage = (pstage + 1 == NSTAGE) ? 0 : pstage + 1;
+                            cpa_wait<NSTAGE - 1>();
+                            unit(C[i], ringw + cstage * 128 + lane, Uk, nctn);
+                            cstage = (cstage + 1 == NSTAGE) ? 0 : cstage + 1;
+                            if (i == 0 && warp < 2 && k == j - 1) publish(C[0], 2 * j + warp, jn, epn);   // block j: U[j, jn] is final
+                        }
+                    }
+                }
+                cpa_wait<0>();
+                if (jn < nb) {                                   // rows below block j -> panel jn (shared, swizzled; slots >= jn are free)
+                    T* PBn = BC + (size_t)jn * 256;
+#pragma unroll
+                    for (int i = 0; i < TPW; ++i) {
+                        const int t = 2 * j + warp + NW * i;
+                        if (i < imax && t >= 2 * jn) {
+#pragma unroll
+                            for (int ct = 0; ct < 2; ++ct)
+#pragma unroll
+                                for (int e = 0; e < 2; ++e) PBn[mphys(8 * (t - 2 * jn) + g, 8 * ct + 2 * tl + e, 16)] = C[i][ct].get(e);
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+            tock(6, t_b, 0);
+        }
+        epoch0 += nb + 2;
+        const long long t_bs = tick();
+
+        // ---- back substitution: x_k = U_kk^-1 (y_k - sum_{k' > k} U[k, k'] x_k'), blocks from the last to the first ----
+        // block b belongs to warp b mod NW; y comes back from the shared slots (B-fragment order).  The U blocks a warp multiplies
+        // with stream through its FIFO one tile ahead (they were written a whole factorisation ago: DRAM latency otherwise).
+        for (int e = tid; e < nb * 256 * (int)sizeof(T) / 128; e += NT)   // the inverted diagonal blocks: pull them into L2
+            asm volatile("prefetch.global.L2 [%0];" :: "l"(UIg + (size_t)e * (128 / sizeof(T))));
+#pragma unroll
+        for (int bi = 0; bi < RBW; ++bi) {
+            const int b = warp + bi * NW;
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+#pragma unroll
+                for (int ct = 0; ct < 2; ++ct)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e)
+                        if (2 * bi + h < TPW) C[2 * bi + h][ct].set(e, b < nb ? BC[b * 256 + bfrag_off(8 * h + g, 8 * ct + 2 * tl + e)] : Num<T>::zero());
+        }
+        // the U blocks of step kq (U[b, kq], b < kq) into L2, a couple of steps before the FIFO asks for them
+        auto l2_prefetch_u = [&](const int kq) {
+            if (kq < 1) return;
+            constexpr int LPB = 256 * (int)sizeof(T) / 128;      // 128-byte lines per block
+            for (int e = tid; e < kq * LPB; e += NT) {
+                const int b = e / LPB, ln = e - b * LPB;
+                asm volatile("prefetch.global.L2 [%0];" :: "l"(Ug + ((long long)b * nb + kq) * 256 + (size_t)ln * (128 / sizeof(T))));
+            }
+        };
+        l2_prefetch_u(nb - 1);
+        l2_prefetch_u(nb - 2);
+        {
+            // units (k, bi, h): k from nb - 1 down to 1, owned blocks b = warp + NW bi < k, the two row tiles of the block
+            int pk = nb - 1, pbi = 0, ph = 0;
+            auto pnorm = [&]() { while (pk >= 1 && (pbi >= RBW || warp + pbi * NW >= pk)) { --pk; pbi = 0; } };
+            auto issue = [&](const int stage) {
+                const T* src = Ug + ((long long)(warp + pbi * NW) * nb + pk) * 256 + ph * 128 + lane;
+                T* dst = ringw + stage * 128 + lane;
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) Num<T>::cp_async(dst + 32 * kk, src + 32 * kk);
+            };
+            auto pnext = [&]() { ph ^= 1; if (ph == 0) ++pbi; pnorm(); };
+            pnorm();
+            int pstage = 0, cstage = 0;
+#pragma unroll
+            for (int st = 0; st < NSTAGE - 1; ++st) {
+                if (pk >= 1) { issue(pstage); pnext(); }
+                cpa_commit();
+                pstage = (pstage + 1 == NSTAGE) ? 0 : pstage + 1;
+            }
+            __syncthreads();
+            for (int k = nb - 1; k >= 0; --k) {
+#pragma unroll
+                for (int bi = 0; bi < RBW; ++bi) {
+                    if (warp + bi * NW == k && 2 * bi + 1 < TPW) {   // x_k = U_kk^-1 (upper triangular inverse) times the finished block
+#pragma unroll
+                        for (int h = 0; h < 2; ++h)
+#pragma unroll
+                            for (int ct = 0; ct < 2; ++ct)
+#pragma unroll
+                                for (int e = 0; e < 2; ++e) xch[bfrag_off(8 * h + g, 8 * ct + 2 * tl + e)] = C[2 * bi + h][ct].get(e);
+                        __syncwarp();
+                        const T* ui = UIg + (long long)k * 256 + lane;
+                        T* slot = BC + k * 256;
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            Acc<T> d0, d1;
+                            d0.zero(); d1.zero();
+#pragma unroll
+                            for (int kk = 0; kk < 4; ++kk) {
+                                if (h == 0 || kk >= 2) {
+                                    const T a = ui[(h * 4 + kk) << 5];
+                                    const T b0 = xch[((kk * 2) << 5) + lane], b1 = xch[((kk * 2 + 1) << 5) + lane];
+                                    d0.mma1(a, b0); if (mct > 1) d1.mma1(a, b1);
+                                    d0.mma2(a, b0); if (mct > 1) d1.mma2(a, b1);
+                                }
+                            }
+#pragma unroll
+                            for (int e = 0; e < 2; ++e) {
+                                slot[bfrag_off(8 * h + g, 2 * tl + e)] = d0.get(e);
+                                slot[bfrag_off(8 * h + g, 8 + 2 * tl + e)] = d1.get(e);
+                            }
+                        }
+                    }
+                }
+                __syncthreads();
+                l2_prefetch_u(k - 2);
+                const T* Xk = BC + k * 256 + lane;
+#pragma unroll
+                for (int bi = 0; bi < RBW; ++bi) {
+                    const int b = warp + bi * NW;
+                    if (b < k && 2 * bi + 1 < TPW) {
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            if (pk >= 1) { issue(pstage); pnext(); }
+                            cpa_commit();
+                            pstage = (pstage + 1 == NSTAGE) ? 0 : pstage + 1;
+                            cpa_wait<NSTAGE - 1>();
+                            const T* af = ringw + cstage * 128 + lane;
+                            cstage = (cstage + 1 == NSTAGE) ? 0 : cstage + 1;
+#pragma unroll
+                            for (int kk = 0; kk < 4; ++kk) {
+                                const T a = Num<T>::neg(af[32 * kk]);
+                                const T b0 = Xk[(kk * 2) << 5], b1 = Xk[(kk * 2 + 1) << 5];
+                                C[2 * bi + h][0].mma1(a, b0); if (mct > 1) C[2 * bi + h][1].mma1(a, b1);
+                                C[2 * bi + h][0].mma2(a, b0); if (mct > 1) C[2 * bi + h][1].mma2(a, b1);
+                            }
+                        }
+                    }
+                }
+            }
+            cpa_wait<0>();
+        }
+        __syncthreads();
+        tock(7, t_bs, 0);
+        auto xs = [&](const int i, const int c) -> T { return BC[(i >> 4) * 256 + bfrag_off(i & 15, c)]; };
+        if (p.X) for (int e = tid; e < r * m; e += NT) { const int i = e / m, c = e - i * m; p.X[pt * (long long)r * m + e] = xs(i, c); }
+        if (p.info && tid == 0) p.info[pt] = *info_sh;
+        if (p.S) {
+            for (int e = warp; e < m * m; e += NW) {
+                const int a = e / m, b = e - a * m;
+                T acc = Num<T>::zero();
+                for (int k = lane; k < r; k += 32) Num<T>::fma_(acc, xs(k, a), Num<T>::scale(cb, __ldg(p.Br + (long long)k * p.ldb + b)));
+                acc = warp_sum(acc);
+                if (lane == 0) p.S[pt * (long long)m * m + e] = Num<T>::jz(p.zs[pt], acc);
+            }
+        }
+        __syncthreads();
+        tock(0, t_pt, 0);
+    }
+}
+
+
 struct LeftGeom { int R, nb, NW, RBW, MINB; size_t smem, slot_elems; int cfg; };
 
 // Geometry per size (cfg): warps per CTA x owned 16-row blocks per warp must cover R / 16 blocks.
 //   1: 4 warps x 2 blocks  (R <= 128)      2: 8 warps x 2 (R <= 256)      3: 16 warps x 2 (R <= 512)
-//   4: 8 warps x 4 (R <= 512; real twin: two CTAs per SM)
+//   4: 8 warps x 4 (R <= 512; real twin: two CTAs per SM)      5: 4 warps x 4 (float64, R <= 256: four CTAs per SM)
 template <typename T>
 LeftGeom left_geom(int r, int m) {
     LeftGeom gm;
     gm.R = (r + 15) / 16 * 16;
     gm.nb = gm.R / 16;
-    int cfg = gm.nb <= 8 ? 1 : (gm.nb <= 16 ? 2 : (sizeof(T) == 8 ? 4 : 3));
-    if (const char* e = getenv("MF_LEFT_CFG")) { const int c = atoi(e); if (c >= 1 && c <= 4) cfg = c; }
-    switch (cfg) {
-        case 1:  gm.NW = 4; gm.RBW = 2; break;
-        case 2:  gm.NW = 8; gm.RBW = 2; break;
-        case 3:  gm.NW = 16; gm.RBW = 2; break;
-        default: gm.NW = 8; gm.RBW = 4; break;
-    }
-    if (gm.NW * gm.RBW < gm.nb) {                                 // a hand-picked geometry that does not cover R: fall back
-        cfg = gm.nb <= 8 ? 1 : (gm.nb <= 16 ? 2 : (sizeof(T) == 8 ? 4 : 3));
-        gm.NW = cfg == 1 ? 4 : (cfg == 3 ? 16 : 8); gm.RBW = cfg == 4 ? 4 : 2;
-    }
+    // measured choice (profiles/r02_sweep_left_variants.md).  complex128: four 4-warp CTAs up to R = 96, two 8-warp CTAs up to 256, one
+    // 16-warp CTA above; float64: four 4-warp CTAs up to 128 (two blocks per warp) and up to 192 (four blocks per warp), three 8-warp
+    // CTAs up to 256, two 8-warp CTAs with four blocks per warp above
+    int cfg;
+    if (sizeof(T) == 16) cfg = gm.nb <= 6 ? 1 : (gm.nb <= 16 ? 2 : 3);
+    else cfg = gm.nb <= 8 ? 1 : (gm.nb <= 12 ? 5 : (gm.nb <= 16 ? 2 : 4));
+    const int cfg_auto = cfg;
+    if (const char* e = getenv("MF_LEFT_CFG")) { const int c = atoi(e); if (c >= 1 && c <= (sizeof(T) == 8 ? 5 : 4)) cfg = c; }
+    auto shape = [&](int c) {
+        switch (c) {
+            case 1:  gm.NW = 4; gm.RBW = 2; break;
+            case 2:  gm.NW = 8; gm.RBW = 2; break;
+            case 3:  gm.NW = 16; gm.RBW = 2; break;
+            case 5:  gm.NW = 4; gm.RBW = 4; break;                // float64 only: four 4-warp CTAs per SM up to R = 256
+            default: gm.NW = 8; gm.RBW = 4; break;
+        }
+    };
+    shape(cfg);
+    if (gm.NW * gm.RBW < gm.nb) { cfg = cfg_auto; shape(cfg); }   // a hand-picked geometry that does not cover R: fall back
     gm.cfg = cfg;
     constexpr int NSTAGE = 2;
     gm.smem = sizeof(T) * ((size_t)gm.R * 16 + (size_t)gm.NW * NSTAGE * 128 + 256 + 2 * (size_t)gm.NW * 8) + sizeof(CandKeyL) * 2 * gm.NW
@@ -1075,11 +1326,21 @@ int left_occupancy(K kern, int threads, const LeftGeom& gm, int* per_sm) {
     return 0;
 }
 
+// Measured on B200 (profiles/r02_sweep_left_variants.md): the look-ahead body wins for complex128 up to R = 192 (+20..40 %) and
+// above R = 256 (+2 %); at R = 208..256 the plain body is ~5 % ahead; float64 (a quarter of the DMMA work, all latency): plain body.
+template <typename T>
+int left_version(const LeftGeom& gm) {
+    if (sizeof(T) == 16) return (gm.R <= 192 || gm.R > 256) ? 3 : 2;
+    return 2;
+}
+
 template <typename T, int NW, int RBW, int MINB>
 int launch_left(SweepParamsL<T> p, const LeftGeom& gm, size_t ws_bytes, cudaStream_t stream) {
-    // MF_LEFT_V1 selects the first version of the kernel body (kept for A/B measurements)
-    static const bool v1 = getenv("MF_LEFT_V1") != nullptr;
-    auto kern = v1 ? sweep_left_kernel<T, NW, RBW, MINB, 2> : sweep_left2_kernel<T, NW, 2 * RBW, MINB, 2>;
+    // which body: the look-ahead one (3) or the plain left-looking one (2); MF_LEFT_VER overrides the measured choice
+    int ver = left_version<T>(gm);
+    if (const char* e = getenv("MF_LEFT_VER")) { const int v = atoi(e); if (v == 2 || v == 3) ver = v; }
+    if (getenv("MF_LEFT_LOOKAHEAD")) ver = 3;
+    auto kern = ver == 3 ? sweep_left3_kernel<T, NW, 2 * RBW, MINB, 2> : sweep_left2_kernel<T, NW, 2 * RBW, MINB, 2>;
     int per_sm = 0;
     if (int rc = left_occupancy(kern, NW * 32, gm, &per_sm)) return rc;
     if (per_sm < 1) MF_FAIL_ARG(7, "left-looking sweep does not fit on an SM for this (r, m)");
@@ -1089,8 +1350,23 @@ int launch_left(SweepParamsL<T> p, const LeftGeom& gm, size_t ws_bytes, cudaStre
     if ((long long)(ws_bytes / slot) < grid) grid = (long long)(ws_bytes / slot);
     if (grid < 1 || !p.ws) MF_FAIL_ARG(21, "workspace too small for the left-looking blocked sweep (see mf_sweep_ws_bytes)");
     p.ws_stride = (long long)gm.slot_elems;
+    p.timing = nullptr;
+    static const bool want_timing = getenv("MF_LEFT_TIMING") != nullptr;     // debugging aid: blocks, prints the phase clocks of CTA 0
+    if (want_timing) { MF_CHECK_CUDA(cudaMalloc(&p.timing, 16 * sizeof(unsigned long long))); MF_CHECK_CUDA(cudaMemsetAsync(p.timing, 0, 16 * 8, stream)); }
     kern<<<(unsigned)grid, NW * 32, gm.smem, stream>>>(p, gm.R);
     MF_CHECK_LAUNCH();
+    if (want_timing) {
+        unsigned long long h[16];
+        MF_CHECK_CUDA(cudaMemcpyAsync(h, p.timing, sizeof(h), cudaMemcpyDeviceToHost, stream));
+        MF_CHECK_CUDA(cudaStreamSynchronize(stream));
+        cudaFree(p.timing);
+        const double pts = (double)((p.F + grid - 1) / grid);
+        fprintf(stderr, "[MF_LEFT_TIMING] r=%d m=%d grid=%lld points/CTA~%.0f  cycles per point: total %.0f | col0 load %.0f | panel %.0f | store+inv %.0f | L~ %.0f | "
+                        "early chain %.0f | phase A %.0f | phase B %.0f | backsub %.0f\n", p.r, p.m, grid, pts, h[0] / pts, h[8] / pts, h[1] / pts, h[2] / pts,
+                h[3] / pts, h[4] / pts, h[5] / pts, h[6] / pts, h[7] / pts);
+        fprintf(stderr, "[MF_LEFT_TIMING]   end of phase A work per point: early warps +1..+3: %.0f %.0f %.0f | panel warps 1..3: %.0f %.0f %.0f\n",
+                h[9] / pts, h[10] / pts, h[11] / pts, h[13] / pts, h[14] / pts, h[15] / pts);
+    }
     if (p.S) return gsm_finish_launch(p.S, p.m, p.F, stream);
     return 0;
 }
@@ -1103,6 +1379,7 @@ int dispatch_left(const SweepParamsL<T>& p, size_t ws_bytes, cudaStream_t stream
         case 1:  return launch_left<T, 4, 2, REAL ? 4 : 4>(p, gm, ws_bytes, stream);
         case 2:  return launch_left<T, 8, 2, REAL ? 3 : 2>(p, gm, ws_bytes, stream);
         case 3:  return launch_left<T, 16, 2, 1>(p, gm, ws_bytes, stream);
+        case 5:  return launch_left<T, 4, 4, REAL ? 4 : 1>(p, gm, ws_bytes, stream);
         default: return launch_left<T, 8, 4, REAL ? 2 : 1>(p, gm, ws_bytes, stream);
     }
 }
@@ -1132,7 +1409,7 @@ int sweep_left_launch_c128(const SweepParams& q, size_t ws_bytes, cudaStream_t s
     SweepParamsL<cplx> p;
     p.A0 = q.A0; p.A1 = q.A1; p.A2 = q.A2; p.lda = q.lda; p.Br = q.Br; p.ldb = q.ldb; p.r = q.r; p.m = q.m;
     p.c0 = q.c0; p.c1 = q.c1; p.c2 = q.c2; p.cb = q.cb; p.zs = q.zs; p.F = q.F; p.X = q.X; p.S = q.S; p.info = q.info;
-    p.ws = q.ws; p.ws_stride = 0;
+    p.ws = q.ws; p.ws_stride = 0; p.timing = nullptr;
     return dispatch_left<cplx>(p, ws_bytes, stream);
 }
 
@@ -1142,6 +1419,6 @@ int sweep_left_launch_f64(const double* A0, const double* A1, const double* A2, 
     SweepParamsL<double> p;
     p.A0 = A0; p.A1 = A1; p.A2 = A2; p.lda = lda; p.Br = Br; p.ldb = ldb; p.r = r; p.m = m;
     p.c0 = c0; p.c1 = c1; p.c2 = c2; p.cb = cb; p.zs = zs; p.F = F; p.X = X; p.S = S; p.info = info;
-    p.ws = (double*)ws; p.ws_stride = 0;
+    p.ws = (double*)ws; p.ws_stride = 0; p.timing = nullptr;
     return dispatch_left<double>(p, ws_bytes, stream);
 }
