@@ -35,9 +35,12 @@ static int pick_variant(int r, int m, int variant) {
     return 1;
 }
 
+// Measured crossover (profiles/r02_sweep_crossover.md): the shared-memory kernel wins up to r = 64 (three 4-warp CTAs per SM), from
+// r = 65 its one 8-warp CTA per SM loses to the left-looking kernel's four 4-warp CTAs (3.9 M against 2.2 M points/s at r = 80).
 static bool blocked_family_uses_left(int r, int m) {
     if (getenv("MF_SWEEP_FORCE_LEFT") && sweep_left_supports_c128(r, m)) return true;
-    return !sweep_blocked_fits_smem(r, m);
+    if (getenv("MF_SWEEP_FORCE_SMEM") && sweep_blocked_fits_smem(r, m)) return false;
+    return !sweep_blocked_fits_smem(r, m) || (r > 64 && sweep_left_supports_c128(r, m));
 }
 
 extern "C" int mf_sweep_variant_supported(int r, int m, int variant) {

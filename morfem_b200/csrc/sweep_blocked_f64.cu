@@ -398,7 +398,9 @@ static bool rblocked_fits(int r, int m) {
 static bool f64_uses_left(int r, int m, int variant) {
     if (variant == 5) return true;
     if (variant == 3) return false;
-    return !rblocked_fits(r, m) || (getenv("MF_SWEEP_FORCE_LEFT") && sweep_left_supports_f64(r, m));
+    if (getenv("MF_SWEEP_FORCE_SMEM") && rblocked_fits(r, m)) return false;
+    // measured crossover (profiles/r02_sweep_crossover.md): shared-memory kernel up to r = 72, left-looking kernel above
+    return !rblocked_fits(r, m) || ((r > 72 || getenv("MF_SWEEP_FORCE_LEFT")) && sweep_left_supports_f64(r, m));
 }
 
 extern "C" int mf_sweep_f64_supported(int r, int m) {

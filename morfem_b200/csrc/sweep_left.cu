@@ -1291,11 +1291,11 @@ LeftGeom left_geom(int r, int m) {
     LeftGeom gm;
     gm.R = (r + 15) / 16 * 16;
     gm.nb = gm.R / 16;
-    // measured choice (profiles/r02_sweep_left_variants.md).  complex128: four 4-warp CTAs up to R = 96, two 8-warp CTAs up to 256, one
+    // measured choice (profiles/r02_sweep_left_variants.md).  complex128: four 4-warp CTAs up to R = 112, two 8-warp CTAs up to 256, one
     // 16-warp CTA above; float64: four 4-warp CTAs up to 128 (two blocks per warp) and up to 192 (four blocks per warp), three 8-warp
     // CTAs up to 256, two 8-warp CTAs with four blocks per warp above
     int cfg;
-    if (sizeof(T) == 16) cfg = gm.nb <= 6 ? 1 : (gm.nb <= 16 ? 2 : 3);
+    if (sizeof(T) == 16) cfg = gm.nb <= 7 ? 1 : (gm.nb <= 16 ? 2 : 3);
     else cfg = gm.nb <= 8 ? 1 : (gm.nb <= 12 ? 5 : (gm.nb <= 16 ? 2 : 4));
     const int cfg_auto = cfg;
     if (const char* e = getenv("MF_LEFT_CFG")) { const int c = atoi(e); if (c >= 1 && c <= (sizeof(T) == 8 ? 5 : 4)) cfg = c; }

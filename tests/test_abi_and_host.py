@@ -165,7 +165,8 @@ def test_streamed_sweep_geometry_from_workspace_sizes(monkeypatch):
         assert lib.mf_sweep_ws_bytes(r, m, 10, 4) == 10 * slot(r, m)          # never more slots than points
     monkeypatch.setenv("MF_STREAM_CFG", "0")
     assert lib.mf_sweep_ws_bytes(256, 4, big, 4) == sms * slot(256, 4)
-    assert lib.mf_sweep_ws_bytes(64, 2, big, 3) <= 256                         # r <= 112: matrix lives in shared memory
+    assert lib.mf_sweep_ws_bytes(64, 2, big, 3) <= 256                         # r <= 64: matrix lives in shared memory
+    assert lib.mf_sweep_ws_bytes(80, 2, 10, 3) == 10 * 16 * (2 * 80 * 80 + 32 * 80)     # above: the left-looking kernel's slots
 
 
 def test_left_looking_sweep_workspace_sizes():
@@ -178,6 +179,6 @@ def test_left_looking_sweep_workspace_sizes():
     for r, m in ((113, 1), (160, 4), (256, 4), (300, 2), (512, 8)):
         assert lib.mf_sweep_ws_bytes(r, m, 10, 5) == 10 * 16 * slot(r)
         assert lib.mf_sweep_ws_bytes(r, m, 10, 3) == 10 * 16 * slot(r)
-        assert lib.mf_sweep_f64_ws_bytes(r, m, 10, 0) == (10 * 8 * slot(r) if r > 128 else 256)     # float64: shared memory holds r <= 128
+        assert lib.mf_sweep_f64_ws_bytes(r, m, 10, 0) == 10 * 8 * slot(r)                          # float64: left-looking kernel from r = 73
         assert lib.mf_sweep_f64_ws_bytes(r, m, 10, 5) == 10 * 8 * slot(r)
     assert lib.mf_sweep_ws_bytes(64, 2, 10, 5) == 10 * 16 * slot(64) and lib.mf_sweep_f64_ws_bytes(64, 2, 10, 5) == 10 * 8 * slot(64)

@@ -243,8 +243,11 @@ def test_real_sweep_equals_complex_sweep_and_oracle(dv, r, m, nf):
         cplx = run_sweep(dv, f, a0, a1, a2, b, cb, variant=variant)          # the complex128 instance of the same kernel
         assert real.x.dtype == torch.float64
         assert not np.any(real.info.cpu().numpy())
-        assert np.all(per_point_rel(real.x.cpu().numpy(), cplx.x.cpu().numpy().real) < 1e-12), variant    # same algorithm, same pivots
-        assert np.all(per_point_rel(real.gsm.cpu().numpy(), cplx.gsm.cpu().numpy()) < 1e-12), variant
+        # same algorithm and pivots (the two element types may run different bodies / CTA geometries of the left-looking kernel,
+        # so the agreement is to rounding times the conditioning of the point, not bit for bit)
+        same = np.maximum(1e-12, 20 * EPS * cond)
+        assert np.all(per_point_rel(real.x.cpu().numpy(), cplx.x.cpu().numpy().real) < same), variant
+        assert np.all(per_point_rel(real.gsm.cpu().numpy(), cplx.gsm.cpu().numpy()) < same), variant
         assert np.all(per_point_rel(real.x.cpu().numpy(), x_ref) < tol), variant
         assert np.all(per_point_rel(real.gsm.cpu().numpy(), s_ref) < tol), variant
 
