@@ -19,12 +19,12 @@ __global__ void __launch_bounds__(EST_THREADS) estimator_kernel(EstParams p) {
     const long long pt = blockIdx.x;
     const cplx* x = p.X + pt * (long long)r * m;
     for (int i = tid; i < r * m; i += EST_THREADS) xs[i] = x[i];
-    for (int i = tid; i < m * m; i += EST_THREADS) E[i] = cmake(0.0, 0.0);
     __syncthreads();
     const double cc[3] = {p.c[0][pt], p.c[1][pt], p.c[2][pt]};
     const double cb = p.cb[pt];
+    // T[i][q] = sum_ab c_a c_b G_ab[i, :] x  -  cb sum_a c_a H_a[i, :]   (r x m), one row per thread, kept in shared memory
+    cplx* T = E + m * m;           // r*m
     for (int i = tid; i < r; i += EST_THREADS) {
-        // t = sum_ab c_a c_b G_ab[i, :] x  -  cb sum_a c_a H_a[i, :]        (1 x m)
         cplx t[MF_MAX_PORTS];
         for (int q = 0; q < m; ++q) t[q] = cmake(0.0, 0.0);
         for (int ab = 0; ab < 9; ++ab) {
@@ -42,20 +42,15 @@ __global__ void __launch_bounds__(EST_THREADS) estimator_kernel(EstParams p) {
             const double w = -cb * cc[a];
             for (int q = 0; q < m; ++q) { cplx h = H[(long long)i * m + q]; t[q].x = fma(w, h.x, t[q].x); t[q].y = fma(w, h.y, t[q].y); }
         }
-        // E[pp][q] += conj(x[i][pp]) * t[q]
-        for (int pp = 0; pp < m; ++pp) {
-            cplx xc = cconj(xs[i * m + pp]);
-            for (int q = 0; q < m; ++q) {
-                cplx v = cmul(xc, t[q]);
-                atomicAdd(&E[pp * m + q].x, v.x); atomicAdd(&E[pp * m + q].y, v.y);
-            }
-        }
+        for (int q = 0; q < m; ++q) T[i * m + q] = t[q];
     }
     __syncthreads();
-    // remaining terms: - cb sum_a c_a H_a^H x + cb^2 BB, then the Frobenius norm
-    if (tid < m * m) {
-        const int pp = tid / m, q = tid - pp * m;
-        cplx acc = E[tid];
+    // E[pp][q] = sum_i conj(x[i][pp]) T[i][q]  - cb sum_a c_a (H_a^H x)[pp][q] + cb^2 BB[pp][q]: one entry per thread, summed in a fixed
+    // order (deterministic estimator values, any m up to MF_MAX_PORTS)
+    for (int e = tid; e < m * m; e += EST_THREADS) {
+        const int pp = e / m, q = e - pp * m;
+        cplx acc = cmake(0.0, 0.0);
+        for (int i = 0; i < r; ++i) cfma(acc, cconj(xs[i * m + pp]), T[i * m + q]);
         for (int a = 0; a < 3; ++a) {
             const cplx* H = p.H[a];
             if (!H) continue;
@@ -64,8 +59,8 @@ __global__ void __launch_bounds__(EST_THREADS) estimator_kernel(EstParams p) {
             for (int k = 0; k < r; ++k) cfma(s, cconj(H[(long long)k * m + pp]), xs[k * m + q]);
             acc.x = fma(w, s.x, acc.x); acc.y = fma(w, s.y, acc.y);
         }
-        if (p.BB) { cplx bb = p.BB[tid]; acc.x = fma(cb * cb, bb.x, acc.x); acc.y = fma(cb * cb, bb.y, acc.y); }
-        E[tid] = acc;
+        if (p.BB) { cplx bb = p.BB[e]; acc.x = fma(cb * cb, bb.x, acc.x); acc.y = fma(cb * cb, bb.y, acc.y); }
+        E[e] = acc;
     }
     __syncthreads();
     if (tid == 0) {
@@ -90,13 +85,12 @@ extern "C" int mf_estimator_c128(const mf_c128* X, int r, int m, int64_t F, cons
     if (!c0 || !c1 || !c2 || !cb) MF_FAIL_ARG(8, "coefficient arrays must not be NULL");
     if (!err) MF_FAIL_ARG(12, "err is NULL");
     if (F == 0) return 0;
-    if (m * m > EST_THREADS) MF_FAIL_ARG(3, "m too large");
     EstParams p;
     for (int i = 0; i < 9; ++i) p.G[i] = (const cplx*)G_host[i];
     for (int i = 0; i < 3; ++i) p.H[i] = (const cplx*)H_host[i];
     p.BB = (const cplx*)BB; p.X = (const cplx*)X; p.c[0] = c0; p.c[1] = c1; p.c[2] = c2; p.cb = cb; p.err = err;
     p.r = r; p.m = m; p.F = F;
-    const size_t smem = sizeof(cplx) * ((size_t)r * m + (size_t)m * m);
+    const size_t smem = sizeof(cplx) * (2 * (size_t)r * m + (size_t)m * m);
     MF_CHECK_CUDA(cudaFuncSetAttribute(estimator_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     estimator_kernel<<<(unsigned)F, EST_THREADS, smem, (cudaStream_t)stream>>>(p);
     MF_CHECK_LAUNCH();
