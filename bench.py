@@ -502,7 +502,7 @@ def run_b200(args, name, wl, rank, world, local_rank):
         tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
         ent = tr.get(f"{name}:{'f64' if real else 'c128'}:{dominant}")
         if ent:
-            traffic, traffic_src = ent["bytes_per_launch_at_bench_size"], ent["source"]
+            traffic, traffic_src = ent["bytes_per_point"] * (f_total / world), ent["source"]
     except Exception:
         pass
     roof = None
