@@ -39,7 +39,7 @@ ERROR_THRESHOLD = 1e-6
 USE_EQUALLY_DISTRIBUTED = False
 EQUALLY_DISTRIBUTED_REDUCTION_RATE = 0.97  # in range <0, 1)
 PLOT_GREEDY_ITERATIONS = False             # accepted for compatibility; plotting is not part of this package
-USE_OPM = False                            # accepted for compatibility; the estimator blocks are always rebuilt on device
+USE_OPM = False                            # True: incremental greedy search (only the new columns are orthonormalised, multiplied and projected)
 TRUNCATION_TOL = 0.0
 VERBOSE = False
 
@@ -266,7 +266,7 @@ def solve_finite_element_method(md: ModelDefinition):
     real = _real_inputs(md.a0, md.a1, md.a2, md.b)        # the reference's reduced models are real: float64 sweep kernel
     up = (lambda a: dv.real_or_complex_to_device(np.asarray(a))) if real else dv.to_device_c128
     ops = [None if _is_zero_operator(a) else up(a) for a in (md.a0, md.a1, md.a2)]
-    b_r = up(md.b)
+    b_r = up(md.b.toarray() if issparse(md.b) else md.b)             # impulse_vector densifies a sparse b (implementation.py:531-533)
     res = _sweep_device(domain, ops, b_r, md.t_a0, md.t_a1, md.t_a2, md.t_b, want_x=True, want_gsm=False)
     x = res.x.cpu().numpy()
     _warn_singular(res.info.cpu().numpy())
@@ -327,6 +327,120 @@ def error_estimator(md: ModelDefinition, q, opm=None, time_stats=None, _ops: Opt
     return err.cpu().numpy()
 
 
+class _GreedyState:
+    """Device-resident state of the incremental greedy search (``USE_OPM = True``, implementation.py:230-263, :275-295, :455-465).
+
+    The reference keeps 16 projected matrices and grows them blockwise with ``expand_matrix`` while the new vectors are
+    Gram-Schmidt-orthonormalised against the base (``orthonormalize_to_base``).  Here the base ``q``, ``a_i^T q`` (for the Galerkin
+    projection) and ``a_i q`` (whose Gram matrices are the estimator blocks ``q^H a_i^H a_j q``) live in column-growing device
+    buffers; a greedy step multiplies, projects and orthonormalises ONLY the new M columns: O(N r M) work instead of O(N r^2)."""
+
+    def __init__(self, md: ModelDefinition, ops: "_DeviceOperators", first_block):
+        from . import device as dv
+        import torch
+        self.dv, self.torch, self.md, self.ops = dv, torch, md, ops
+        self.live = [i for i in range(3) if not ops.zero[i]]
+        qd, _ = _orthonormal_basis_device(first_block, md)                  # implementation.py:222-226
+        self.n, self.dtype, self.dev = qd.shape[0], qd.dtype, qd.device
+        self.m = md.b.shape[1]
+        self.cap, self.r = 0, 0
+        self.q = None
+        self.yt = {i: None for i in self.live}                               # a_i^T q
+        self.y = {i: None for i in self.live}                                # a_i q
+        self.a_r = {i: torch.zeros((0, 0), dtype=self.dtype, device=self.dev) for i in self.live}
+        self.g = {(a, b): torch.zeros((0, 0), dtype=self.dtype, device=self.dev) for a in self.live for b in self.live}
+        self.hb = {i: torch.zeros((0, self.m), dtype=self.dtype, device=self.dev) for i in self.live}
+        self.b_r = torch.zeros((0, self.m), dtype=self.dtype, device=self.dev)
+        self.bb = dv.to_device_c128((h(ops.b_host) @ ops.b_host).toarray())
+        self._append_orthonormal(qd)
+
+    def _reserve(self, cols: int):
+        if cols <= self.cap:
+            return
+        torch = self.torch
+        cap = max(cols, 2 * self.cap, 16)
+
+        def grow(old):
+            new = torch.empty((self.n, cap), dtype=self.dtype, device=self.dev)
+            if old is not None and self.r:
+                new[:, :self.r].copy_(old[:, :self.r])
+            return new
+        self.q = grow(self.q)
+        for i in self.live:
+            self.yt[i], self.y[i] = grow(self.yt[i]), grow(self.y[i])
+        self.cap = cap
+
+    def _append_orthonormal(self, v):
+        """``v`` (N x k, orthonormal and orthogonal to the base): SpMMs, projections and Gram blocks of the new columns only."""
+        dv, torch = self.dv, self.torch
+        r, k = self.r, v.shape[1]
+        self._reserve(r + k)
+        self.q[:, r:r + k].copy_(v)
+        v = self.q[:, r:r + k]
+        q_old, q_all = self.q[:, :r], self.q[:, :r + k]
+        for i in self.live:
+            dv.spmm(self.ops.at[i], v.contiguous(), out=self.yt[i][:, r:r + k])
+            dv.spmm(self.ops.a_csr(i), v.contiguous(), out=self.y[i][:, r:r + k])
+
+        def grown(old, right, bottom_left):
+            """[[old, right_top], [bottom_left, right_bottom]] -- expand_matrix (implementation.py:455-465)"""
+            new = torch.empty((r + k, r + k), dtype=self.dtype, device=self.dev)
+            new[:r, :r].copy_(old)
+            new[:, r:].copy_(right)
+            if r:
+                new[r:, :r].copy_(bottom_left)
+            return new
+        vc = v.contiguous()
+        for i in self.live:
+            right = dv.gemm_tn(self.yt[i][:, :r + k], vc, conj=False)                          # q_all^T a_i v
+            bl = dv.gemm_tn(self.yt[i][:, r:r + k].contiguous(), q_old, conj=False) if r else None   # v^T a_i q_old
+            self.a_r[i] = grown(self.a_r[i], right, bl)
+        for a in self.live:
+            for b in self.live:
+                right = dv.gemm_tn(self.y[a][:, :r + k], self.y[b][:, r:r + k].contiguous(), conj=True)
+                bl = dv.gemm_tn(self.y[a][:, r:r + k].contiguous(), self.y[b][:, :r], conj=True) if r else None
+                self.g[(a, b)] = grown(self.g[(a, b)], right, bl)
+            self.hb[a] = torch.cat((self.hb[a], dv.project_rhs(self.ops.b, self.y[a][:, r:r + k].contiguous(), 0, conj=True)), dim=0)
+        self.b_r = torch.cat((self.b_r, dv.project_rhs(self.ops.b, vc, 0, conj=False)), dim=0)
+        self.r = r + k
+
+    def append(self, vectors):
+        """``orthonormalize_to_base`` (implementation.py:491-508) for a block of new full-order solutions: two block Gram-Schmidt
+        passes against the base (the second removes what rounding left of the first), then the block itself is orthonormalised
+        (CholeskyQR2 + SVD of R); then the state grows by the new columns."""
+        dv = self.dv
+        v = _block_to_device(vectors, self.md)
+        if v.dtype != self.dtype:
+            raise _ffi_error("incremental greedy search: a complex solution joined a real basis (set USE_OPM = False for such models)")
+        q_old = self.q[:, :self.r]
+        for _ in range(2):
+            c = dv.gemm_tn(q_old, v, conj=True)                              # coefficients against the base
+            v = v - dv.gemm_nn(q_old, c)
+        v, _ = dv.orthonormalize(v.contiguous(), truncation_tol=TRUNCATION_TOL)
+        self._append_orthonormal(v)
+
+    def error_estimator(self):
+        """implementation.py:348-452 with the blocks taken from the state (the reference's ``USE_OPM`` branch, :351-367)."""
+        dv, torch, md = self.dv, self.torch, self.md
+        ops_r = [self.a_r.get(i) for i in range(3)]
+        res = _sweep_device(md.domain, ops_r, self.b_r, md.t_a0, md.t_a1, md.t_a2, md.t_b, want_x=True, want_gsm=False)
+        dom = np.asarray(md.domain, dtype=np.float64)
+        c = [torch.from_numpy(coefficient_array(f, dom)).to(self.dev) for f in (md.t_a0, md.t_a1, md.t_a2, md.t_b)]
+        c128 = lambda t: t if (t is None or t.is_complex()) else t.to(torch.complex128)      # noqa: E731
+        g = [[c128(self.g[(a, b)].contiguous()) if (a in self.live and b in self.live) else None for b in range(3)] for a in range(3)]
+        hb = [c128(self.hb[a].contiguous()) if a in self.live else None for a in range(3)]
+        err = dv.estimator(res.x if res.x.is_complex() else res.x.to(torch.complex128), g, hb, self.bb, c[0], c[1], c[2], c[3])
+        return err.cpu().numpy()
+
+    def basis(self):
+        return self.q[:, :self.r].contiguous()
+
+
+def _ffi_error(msg):
+    from ._ffi import MorfemB200Error
+    return MorfemB200Error(msg)
+
+
 def new_solution_for_projection_base(md: ModelDefinition, q, opm=None, time_stats=None, _ops=None):
     """implementation.py:321-328"""
     error = error_estimator(md, q, opm, time_stats, _ops=_ops)
@@ -343,6 +457,18 @@ def projection_base(md: ModelDefinition, _return_device: bool = False):
     from . import device as dv
     ops = _DeviceOperators(md)
     initial_vectors = np.hstack((solve_fem_point(md.domain[0], md), solve_fem_point(md.domain[-1], md)))
+    if USE_OPM:                                   # incremental search: implementation.py:230-263 (set-up), :275-295 (growth)
+        state = _GreedyState(md, ops, initial_vectors)
+        projection_base.last_errors = []
+        while True:
+            error = state.error_estimator()
+            projection_base.last_errors.append(error)
+            idx_max = error.argmax()
+            if error[idx_max] < ERROR_THRESHOLD:
+                break
+            state.append(solve_fem_point(md.domain[idx_max], md))
+        qd = state.basis()
+        return qd if _return_device else _basis_to_host(qd, md)
     qd, _ = _orthonormal_basis_device(initial_vectors, md)
     while True:
         q_new, _error = new_solution_for_projection_base(md, qd, _ops=ops)
@@ -355,6 +481,82 @@ def projection_base(md: ModelDefinition, _return_device: bool = False):
         stacked = torch.cat((qd, new), dim=1).contiguous()
         qd, _ = dv.orthonormalize(stacked, truncation_tol=TRUNCATION_TOL)
     return qd if _return_device else _basis_to_host(qd, md)
+
+
+# ---- host helpers of the reference kept for API completeness (none of them sits on the hot path) ---------------------------------------
+class OfflinePhaseMatrices:
+    """implementation.py:57-73: holder of the 16 projected estimator matrices of the ``USE_OPM`` mode.  The device path keeps them in
+    ``_GreedyState``; this record only exists so that reference code constructing one keeps working."""
+    qh_a0h_a0_q = qh_a0h_a1_q = qh_a0h_a2_q = qh_a0h_b = None
+    qh_a1h_a0_q = qh_a1h_a1_q = qh_a1h_a2_q = qh_a1h_b = None
+    qh_a2h_a0_q = qh_a2h_a1_q = qh_a2h_a2_q = qh_a2h_b = None
+    bh_a0_q = bh_a1_q = bh_a2_q = bh_b = None
+
+
+class TimeStatistics:
+    """implementation.py:76-96: wall-clock buckets (the class-level dict of the reference, shared by all instances, included)."""
+    times = {}
+
+    def __init__(self):
+        self.clock = time.time()
+
+    def start_clock(self):
+        self.clock = time.time()
+
+    def add_time(self, name):
+        now = time.time()
+        self.times[name] = self.times.get(name, 0.0) + now - self.clock
+        self.clock = now
+
+    def add_custom_time(self, name, since):
+        self.times[name] = self.times.get(name, 0.0) + time.time() - since
+
+    def print_statistics(self):
+        whole = self.times.get("Whole", sum(self.times.values())) or 1.0
+        for name, t in self.times.items():
+            print(f"{name}: {t:.3f} s ({100.0 * t / whole:.1f} %)")
+
+
+def orthonormalize_vector_to_base(vector: np.ndarray, base: np.ndarray) -> np.ndarray:
+    """implementation.py:511-523: one classical Gram-Schmidt pass of ``vector`` against the orthonormal columns of ``base``."""
+    if vector.ndim != 1 or base.ndim != 2:
+        raise Exception("vector has to be one-dimensional and base has to be two-dimensional")
+    out = vector - base @ (base.T @ vector)          # sum of the projections on the (normalised) base vectors, no conjugate as in :518
+    return out / np.linalg.norm(out)
+
+
+def orthonormalize_to_base(vectors: np.ndarray, base: np.ndarray) -> np.ndarray:
+    """implementation.py:491-508: the new vectors one after the other, each against the base extended by its predecessors."""
+    if vectors.ndim != 2:
+        raise Exception("new_vectors has to be two-dimensional")
+    if base is not None and base.ndim != 2:
+        raise Exception("base has to be two-dimensional or None")
+    cols = []
+    for i in range(vectors.shape[1]):
+        col = orthonormalize_vector_to_base(vectors[:, i], base)
+        base = np.hstack((base, col[:, None]))
+        cols.append(col)
+    return np.stack(cols, axis=1)
+
+
+def expand_matrix(original: np.ndarray, old_q: np.ndarray, middle, new_part_q: np.ndarray):
+    """implementation.py:455-465: ``[q | q_new]^H middle [q | q_new]`` from its leading block ``original = q^H middle q``."""
+    return np.block([[original, h(old_q) @ middle @ new_part_q],
+                     [h(new_part_q) @ middle @ old_q, h(new_part_q) @ middle @ new_part_q]])
+
+
+def residual_norm(md: ModelDefinition, q: np.ndarray) -> np.ndarray:
+    """implementation.py:331-345 (never called by the reference itself): true residual ``|| A(t) q x - t_b(t) b ||`` per domain point,
+    with the reduced model solved on the device."""
+    ops = _DeviceOperators(md)
+    qd = _block_to_device(q, md)
+    a0_r, a1_r, a2_r, b_r = ops.project(qd)
+    res = _sweep_device(md.domain, [a0_r, a1_r, a2_r], b_r, md.t_a0, md.t_a1, md.t_a2, md.t_b, want_x=True, want_gsm=False)
+    x = res.x.cpu().numpy()
+    out = np.empty(np.asarray(md.domain).size)
+    for i, t in enumerate(np.asarray(md.domain)):
+        out[i] = np.linalg.norm(system_matrix(t, md) @ (np.asarray(q) @ x[i]) - impulse_vector(t, md))
+    return out
 
 
 def morfem_from_snapshots(snapshots: np.ndarray, domain: np.ndarray, a0: csc_array, a1: csc_array, a2: csc_array, b: csc_array,

@@ -16,6 +16,7 @@ Cases
                     block, so lines 178-186 (projection + reduced sweep) run verbatim; then the GSM loop.
   equidist_n600     ``USE_EQUALLY_DISTRIBUTED = True`` path (``implementation.py:197-214``) end to end.
   reduced_rXX_mY    ``solve_finite_element_method`` + ``generalized_scattering_matrix`` on seeded reduced models.
+  opm_n600          the greedy search with ``USE_OPM = True`` (incremental Gram-Schmidt + blockwise growth of the estimator matrices).
   estimator_n600    ``implementation.error_estimator`` (:348-452) itself, called on the orthonormalised bases a greedy run
                     passes through (r = 4, 6, 8, 10; 2 ports) and on a 3-port model: the per-point residual estimate the
                     greedy search takes its arg-max of, plus the size of the largest term of the 16-term sum (the estimate
@@ -187,9 +188,45 @@ def case_estimator():
     save("estimator_n600", grid=np.array([5, 4, 30]), face=np.array(19), **out)
 
 
+def case_opm():
+    """The greedy search with USE_OPM = True (implementation.py:16, :230-295): new vectors Gram-Schmidt-orthonormalised against the base,
+    the 16 estimator matrices grown blockwise.  Records the estimator curve of every iteration, the final basis size and the ROM S-parameters."""
+    ct, tt = synthetic.waveguide_operators(5, 4, 30)
+    n = ct.shape[0]
+    wp = synthetic.port_matrix(n, 2, 19)
+    in_c, in_gamma, in_b = synthetic.driver_scaled(ct, tt, wp)
+    f = np.linspace(3e9, 5e9, 60)
+    md = ref_impl.ModelDefinition(f, in_c, csc_array(in_c.shape), in_gamma, in_b, lambda t: 1, lambda t: t,
+                                  lambda t: t ** 2, lambda t: ref_help.b_coefficient(t))
+    errors = []
+    real_new = ref_impl.new_solution_for_projection_base
+
+    def recording(md_, q_, opm_, ts_):
+        q_new, err = real_new(md_, q_, opm_, ts_)
+        errors.append(np.array(err))
+        return q_new, err
+
+    ref_impl.USE_OPM = True
+    ref_impl.new_solution_for_projection_base = recording
+    try:
+        x, q, a0_r, a1_r, a2_r, b_r = quiet(ref_impl.morfem, f, in_c, csc_array(in_c.shape), in_gamma, in_b,
+                                            t_b=lambda t: ref_help.b_coefficient(t))
+    finally:
+        ref_impl.USE_OPM = False
+        ref_impl.new_solution_for_projection_base = real_new
+    gsm = np.stack([ref_help.generalized_scattering_matrix(f[i], x[i], ref_help.b_coefficient(f[i]) * b_r) for i in range(f.size)])
+    gsm_full = quiet(ref_help.finite_element_method_gsm, f, 2, in_c, in_gamma, in_b)
+    save("opm_n600", grid=np.array([5, 4, 30]), ports=np.array(2), face=np.array(19), f=f, basis_size=np.array(q.shape[1]),
+         errors=np.stack(errors), gsm_rom=gsm, gsm_full=gsm_full,
+         scale=np.array([ref_help.b_coefficient(t) ** 2 for t in f]) * np.linalg.norm((in_b.T @ in_b).toarray()))
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "estimator":
         case_estimator()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "opm":
+        case_opm()
         sys.exit(0)
     case_cfg1()
     case_stages()
@@ -198,3 +235,4 @@ if __name__ == "__main__":
                              (256, 4, 4, 7)]:
         case_reduced(r, m, npts, seed)
     case_estimator()
+    case_opm()

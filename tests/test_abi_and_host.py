@@ -182,3 +182,27 @@ def test_left_looking_sweep_workspace_sizes():
         assert lib.mf_sweep_f64_ws_bytes(r, m, 10, 0) == 10 * 8 * slot(r)                          # float64: left-looking kernel from r = 73
         assert lib.mf_sweep_f64_ws_bytes(r, m, 10, 5) == 10 * 8 * slot(r)
     assert lib.mf_sweep_ws_bytes(64, 2, 10, 5) == 10 * 16 * slot(64) and lib.mf_sweep_f64_ws_bytes(64, 2, 10, 5) == 10 * 8 * slot(64)
+
+
+def test_reference_host_helpers_of_the_opm_mode():
+    """orthonormalize_to_base / orthonormalize_vector_to_base / expand_matrix / OfflinePhaseMatrices / TimeStatistics
+    (implementation.py:57-96, :455-523) keep their names and semantics (host helpers, outside the hot path)."""
+    rng = np.random.default_rng(3)
+    base = np.linalg.qr(rng.standard_normal((40, 5)))[0]
+    v = rng.standard_normal((40, 3))
+    one = impl.orthonormalize_vector_to_base(v[:, 0], base)
+    ref = v[:, 0] - sum(base[:, i] * np.inner(v[:, 0], base[:, i]) for i in range(5))        # implementation.py:517-521
+    assert np.allclose(one, ref / np.linalg.norm(ref), rtol=0, atol=1e-15)
+    new = impl.orthonormalize_to_base(v, base)
+    assert new.shape == (40, 3) and np.abs(base.T @ new).max() < 1e-14 and np.abs(new.T @ new - np.eye(3)).max() < 1e-14
+    mid = rng.standard_normal((40, 40))
+    full = np.hstack((base, new))
+    assert np.allclose(impl.expand_matrix(base.T @ mid @ base, base, mid, new), full.T @ mid @ full, rtol=0, atol=1e-13)
+    with pytest.raises(Exception):
+        impl.orthonormalize_to_base(v[:, 0], base)
+    with pytest.raises(Exception):
+        impl.orthonormalize_vector_to_base(v, base)
+    assert impl.OfflinePhaseMatrices().bh_b is None
+    ts = impl.TimeStatistics()
+    ts.start_clock(); ts.add_time("Offline"); ts.add_custom_time("Whole", ts.clock)
+    assert "Offline" in impl.TimeStatistics.times                 # class-level dict, shared like the reference's (implementation.py:77)

@@ -438,3 +438,32 @@ def test_error_estimator_matches_live_reference_values():
             assert err.shape == ref.shape
             assert np.all(np.abs(err - ref) <= 1e-8 * ref + 200 * eps * scale), (tag, it, float(np.abs(err - ref).max()))
             assert int(err.argmax()) == int(ref.argmax())
+
+
+def test_incremental_greedy_search_matches_live_reference_opm_mode(monkeypatch):
+    """``USE_OPM = True`` (implementation.py:16, :230-295): the greedy search that orthonormalises, multiplies and projects only the
+    new columns and grows the estimator blocks, against the live reference run in the same mode (tests/golden/opm_n600.npz): the
+    estimator curve of every iteration (1e-8 above its cancellation floor), the same points picked, the same final basis size,
+    and ROM S-parameters as close to the full-order ones as the reference's."""
+    from scipy.sparse import csc_array
+    from morfem_b200 import implementation as impl, test_helpers as th, synthetic
+    g = np.load(os.path.join(GOLDEN, "opm_n600.npz"))
+    ct, tt = synthetic.waveguide_operators(*(int(v) for v in g["grid"]))
+    wp = synthetic.port_matrix(ct.shape[0], int(g["ports"]), int(g["face"]))
+    in_c, in_gamma, in_b = synthetic.driver_scaled(ct, tt, wp)
+    f = g["f"]
+    monkeypatch.setattr(impl, "USE_OPM", True)
+    gsm = th.finite_element_method_model_order_reduction_gsm(f, 2, in_c, in_gamma, in_b)
+    errs = impl.projection_base.last_errors
+    eps = np.finfo(float).eps
+    assert len(errs) == g["errors"].shape[0]
+    for it, (err, ref) in enumerate(zip(errs, g["errors"])):
+        assert np.all(np.abs(err - ref) <= 1e-8 * ref + 200 * eps * g["scale"]), (it, float(np.abs(err - ref).max()))
+        assert int(err.argmax()) == int(ref.argmax())
+    d_new = np.linalg.norm((gsm - g["gsm_full"]).reshape(f.size, -1), axis=1)
+    d_ref = np.linalg.norm((g["gsm_rom"] - g["gsm_full"]).reshape(f.size, -1), axis=1)
+    assert d_new.max() <= max(2 * d_ref.max(), 1e-9)
+    # the non-incremental default walks through the same points (same estimator, whole-basis re-orthonormalisation instead)
+    monkeypatch.setattr(impl, "USE_OPM", False)
+    gsm2 = th.finite_element_method_model_order_reduction_gsm(f, 2, in_c, in_gamma, in_b)
+    assert np.abs(gsm2 - gsm).max() < 1e-6
