@@ -1394,7 +1394,10 @@ bool left_supports(int r, int m) {
 template <typename T>
 size_t left_ws_bytes(int r, int m, long long F) {
     const LeftGeom gm = left_geom<T>(r, m);
-    long long grid = (long long)mf_num_sms() * 4; if (grid > F) grid = F; if (grid < 1) grid = 1;   // at most 4 CTAs per SM in any geometry
+    // resident CTAs per SM of the geometry (the __launch_bounds__ the kernels are built with; the launcher clamps its grid to the slots it is given)
+    constexpr bool REAL = sizeof(T) == 8;
+    const int per_sm = gm.cfg == 1 ? 4 : gm.cfg == 2 ? (REAL ? 3 : 2) : gm.cfg == 3 ? 1 : gm.cfg == 5 ? 4 : (REAL ? 2 : 1);
+    long long grid = (long long)mf_num_sms() * per_sm; if (grid > F) grid = F; if (grid < 1) grid = 1;
     return sizeof(T) * gm.slot_elems * (size_t)grid;
 }
 

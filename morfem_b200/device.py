@@ -565,6 +565,8 @@ class BasisInfo:
         self._sweeps = jacobi_sweeps   # device tensor or int
         self.kept = kept               # columns kept after truncation
         self.flags = None              # optimistic CholeskyQR2: device flag blocks awaiting verification
+        self.converged = True          # False when the adaptive Cholesky-QR loop stopped at max_passes
+        self.departure = None          # departure from orthonormality seen by the last adaptive pass
         self.q_ready = None            # basis_and_projection(defer_q=True): event to wait for before q is used
         self.keepalive = None          # ... and the operands of the side-stream product, released after that wait
 
@@ -655,6 +657,8 @@ class CholQR:
     passes: int
     shifts: list
     flags: Optional[torch.Tensor] = None     # optimistic mode: (passes, 32) uint8 flag blocks still to be verified
+    converged: bool = True                   # adaptive mode: False when max_passes ended the loop (a RuntimeWarning was raised)
+    departure: Optional[float] = None        # adaptive mode: max |G_ij - delta_ij| of the equilibrated Gram matrix of the last pass
 
 
 def flags_ok(flags_host: torch.Tensor) -> bool:
@@ -732,9 +736,14 @@ def cholesky_qr(s: torch.Tensor, group=None, max_passes: int = 6, optimistic: bo
         # R = Rtilde D^-1 (undo the equilibration), Rinv = R^-1
         rinv = _unequilibrate(gw, d, rinv_eq)
         r_tot = gw if r_tot is None else gemm_nn(gw, r_tot)
-        final = (departure < 0.1 and shift == 0.0) or p == max_passes - 1
-        if final:
-            return CholQR(x, r_tot, rinv, p + 1, shifts)
+        converged = departure < 0.1 and shift == 0.0
+        if converged or p == max_passes - 1:
+            if not converged:
+                import warnings
+                warnings.warn(f"orthonormalize: the Cholesky-QR passes did not reach a near-orthonormal block after {max_passes} passes "
+                              f"(departure {departure:.2e}, last shift {shift:.1e}); the basis may be less orthonormal than the reference's SVD "
+                              "(snapshot block numerically rank deficient)", RuntimeWarning, stacklevel=3)
+            return CholQR(x, r_tot, rinv, p + 1, shifts, None, converged, departure)
         tgt = p % 2
         if bufs[tgt] is None:
             bufs[tgt] = torch.empty((n_loc, r), dtype=s.dtype, device=dev)
@@ -775,7 +784,9 @@ def basis_rotation(cq: CholQR, truncation_tol: float = 0.0) -> tuple[torch.Tenso
         if sig[0] > 0.0:
             keep = max(1, int(np.count_nonzero(sig > truncation_tol * sig[0])))
     w = gemm_nn(cq.rinv, u[:, :keep] if keep < r else u)
-    return w, BasisInfo(sigma, cq.passes, cq.shifts, sweeps, keep)
+    info = BasisInfo(sigma, cq.passes, cq.shifts, sweeps, keep)
+    info.converged, info.departure = cq.converged, cq.departure
+    return w, info
 
 
 def orthonormalize(s: torch.Tensor, truncation_tol: float = 0.0, group=None, n_global: Optional[int] = None,
