@@ -94,6 +94,7 @@ struct SweepParamsL {
     int* info;    // F or NULL
     T* ws; long long ws_stride;   // per-CTA workspace slots (elements)
     unsigned long long* timing;   // debugging aid (MF_LEFT_TIMING): per-phase clock64 sums of CTA 0, or NULL
+    int remap;                    // look-ahead body: panel warps on SM sub-partitions 0/1, run-ahead warps on 2/3 (MF_LEFT_REMAP)
 };
 
 struct CandKeyL { double v; int pos; int pad; };
@@ -130,6 +131,13 @@ __device__ __forceinline__ void csync() {
     else asm volatile("bar.sync 1, %0;" :: "n"(BARN) : "memory");
 }
 
+#ifdef MF_PANEL_CLOCKS
+__device__ unsigned long long g_panel_clk[8];     // diagnostic build only: clock64 sums of the stages of a panel column step (CTA 0, thread 0)
+#define PCLK(i) do { if (blockIdx.x == 0 && tid == 0) { const long long now_ = clock64(); g_panel_clk[i] += (unsigned long long)(now_ - pc_); pc_ = now_; } } while (0)
+#else
+#define PCLK(i) do { } while (0)
+#endif
+
 template <typename T, int SL, int NW, int BARN = 0>
 __device__ __forceinline__ void panel_factor_t(T* PB, const int LDp, const int rows, const int row0, const int tid,
                                                CandKeyL* candk, T* candrow, int* pvl, int* info_sh, const int info_base) {
@@ -155,9 +163,13 @@ __device__ __forceinline__ void panel_factor_t(T* PB, const int LDp, const int r
 #pragma unroll
         for (int c = 0; c < 8; ++c) a[s][c] = act[s] ? src[c ^ sw] : Num<T>::zero();
     }
+#ifdef MF_PANEL_CLOCKS
+    long long pc_ = clock64();
+#endif
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         const int Tg = row0 + j;
+        PCLK(6);                                                 // tail of the previous column's update
         double vb = act[0] ? Num<T>::abs1(a[0][j]) : -1.0;
         int pbest = pos[0], bs = 0;
         T cand = a[0][j];
@@ -180,6 +192,7 @@ __device__ __forceinline__ void panel_factor_t(T* PB, const int LDp, const int r
                 own = own && (pbest == pmin);
             }
         }
+        PCLK(0);                                                 // candidate + warp arg-max
         CandKeyL* ck = candk + (j & 1) * NW;
         T* cr = candrow + (j & 1) * NW * 8;
         if (own) {                                               // this warp's candidate: key and finished row
@@ -191,7 +204,9 @@ __device__ __forceinline__ void panel_factor_t(T* PB, const int LDp, const int r
                     for (int c = 0; c < 8; ++c) cr[warp * 8 + c] = (c == j) ? rc : a[s][c];
                 }
         }
+        PCLK(1);                                                 // reciprocal + candidate row to shared memory
         csync<BARN>();
+        PCLK(2);                                                 // barrier
         // global winner among the NW warp candidates: lane w looks at candidate w, then the same warp arg-max
         double cv = -2.0; int cp = 0x7fffffff;
         if (lane < nact) {
@@ -215,6 +230,7 @@ __device__ __forceinline__ void panel_factor_t(T* PB, const int LDp, const int r
         const int gw = __ffs(__ballot_sync(FULL, cown)) - 1;
         const int P = __shfl_sync(FULL, cp, gw);
         const double gv = __shfl_sync(FULL, cv, gw);
+        PCLK(3);                                                 // second-level arg-max
         if (own && warp == gw) {                                 // this lane held the pivot row: retire the slot
 #pragma unroll
             for (int s = 0; s < SL; ++s) if (s == bs) act[s] = false;
@@ -229,6 +245,7 @@ __device__ __forceinline__ void panel_factor_t(T* PB, const int LDp, const int r
             PB[Tg * LDp + row0 + (tid ^ swz(j))] = v;
         }
         if (tid == 8) { pvl[j] = P; if (!(gv > 0.0) && *info_sh == 0) *info_sh = info_base + Tg + 1; }
+        PCLK(4);                                                 // pivot row back from shared memory
 #pragma unroll
         for (int s = 0; s < SL; ++s) {
             const T nl = Num<T>::neg(Num<T>::mul(a[s][j], rcp));  // negated multiplier
@@ -237,6 +254,7 @@ __device__ __forceinline__ void panel_factor_t(T* PB, const int LDp, const int r
             for (int c = j + 1; c < 8; ++c) Num<T>::fma_(a[s][c], nl, u[c]);
             if (pos[s] == Tg) pos[s] = P;
         }
+        PCLK(5);                                                 // update issued
     }
 #pragma unroll
     for (int s = 0; s < SL; ++s) {
@@ -796,7 +814,14 @@ __global__ void __launch_bounds__(NW * 32, MINB) sweep_left3_kernel(SweepParamsL
     constexpr int NWE = NW - NWP;                                // warps that run ahead during the panel
     constexpr int SLP = (TPW + 1) / 2;                           // rows per panel thread (R <= 8 NW TPW, NTP threads)
     constexpr int RBW = (TPW + 1) / 2;                           // 16-row blocks per warp in the back substitution
-    const int r = p.r, m = p.m, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // warp roles: hardware warp w issues on SM sub-partition w % 4.  With p.remap the panel warps are the hardware warps with bit 1
+    // clear (sub-partitions 0 and 1) and the run-ahead warps the others, so the scalar FP64 work of the panel does not queue behind
+    // the DMMAs of this CTA's own chain
+    const int lane = threadIdx.x & 31, hw = threadIdx.x >> 5;
+    const int sp = hw & 3, qd = hw >> 2;
+    const int warp = !p.remap ? hw : (sp < 2 ? qd * 2 + sp : NWP + qd * 2 + (sp - 2));
+    const int tid = warp * 32 + lane;
+    const int r = p.r, m = p.m;
     const int g = lane >> 2, tl = lane & 3;
     const int nb = R >> 4, ntiles = R >> 3;
     const int mct = (m + 7) >> 3;
@@ -1351,6 +1376,9 @@ int launch_left(SweepParamsL<T> p, const LeftGeom& gm, size_t ws_bytes, cudaStre
     if (grid < 1 || !p.ws) MF_FAIL_ARG(21, "workspace too small for the left-looking blocked sweep (see mf_sweep_ws_bytes)");
     p.ws_stride = (long long)gm.slot_elems;
     p.timing = nullptr;
+    // panel warps on their own SM sub-partitions: measured +10 % at R = 128, a loss from R = 192 up (profiles/r02_sweep_left_variants.md)
+    static const int env_remap = getenv("MF_LEFT_REMAP") ? atoi(getenv("MF_LEFT_REMAP")) : -1;
+    p.remap = env_remap >= 0 ? (env_remap != 0) : (NW == 8 && gm.R <= 128);
     static const bool want_timing = getenv("MF_LEFT_TIMING") != nullptr;     // debugging aid: blocks, prints the phase clocks of CTA 0
     if (want_timing) { MF_CHECK_CUDA(cudaMalloc(&p.timing, 16 * sizeof(unsigned long long))); MF_CHECK_CUDA(cudaMemsetAsync(p.timing, 0, 16 * 8, stream)); }
     kern<<<(unsigned)grid, NW * 32, gm.smem, stream>>>(p, gm.R);
@@ -1366,6 +1394,15 @@ int launch_left(SweepParamsL<T> p, const LeftGeom& gm, size_t ws_bytes, cudaStre
                 h[3] / pts, h[4] / pts, h[5] / pts, h[6] / pts, h[7] / pts);
         fprintf(stderr, "[MF_LEFT_TIMING]   end of phase A work per point: early warps +1..+3: %.0f %.0f %.0f | panel warps 1..3: %.0f %.0f %.0f\n",
                 h[9] / pts, h[10] / pts, h[11] / pts, h[13] / pts, h[14] / pts, h[15] / pts);
+#ifdef MF_PANEL_CLOCKS
+        unsigned long long pc[8];
+        MF_CHECK_CUDA(cudaMemcpyFromSymbol(pc, g_panel_clk, sizeof(pc)));
+        const double cols = pts * gm.R;
+        fprintf(stderr, "[MF_PANEL_CLOCKS] cycles per pivot column: arg-max %.0f | recip + candidate row %.0f | barrier %.0f | second arg-max %.0f | pivot row read %.0f | "
+                        "update issue %.0f | update tail %.0f\n", pc[0] / cols, pc[1] / cols, pc[2] / cols, pc[3] / cols, pc[4] / cols, pc[5] / cols, pc[6] / cols);
+        memset(pc, 0, sizeof(pc));
+        MF_CHECK_CUDA(cudaMemcpyToSymbol(g_panel_clk, pc, sizeof(pc)));
+#endif
     }
     if (p.S) return gsm_finish_launch(p.S, p.m, p.F, stream);
     return 0;
