@@ -398,8 +398,9 @@ def run_b200(args, name, wl, rank, world, local_rank):
     if use_graph:
         launches = args.steps * path.launches_per_graph          # a replay launches the captured kernels without passing the ABI counter
     value = f_total / (ms_step * 1e-3)
-    gsm_dev = out[0]
-    reduced_dev = out[2]
+    gsm_dev = out[0].clone()                                   # small copies: `out` pins the static outputs of the captured step
+    reduced_dev = [None if o is None else o.clone() for o in out[2]]
+    del out
 
     # ---- parity of the timed configuration against the CPU restatement of the reference (rank 0, sampled points)
     parity, cpu_baseline = None, None
@@ -590,6 +591,9 @@ def run_b200(args, name, wl, rank, world, local_rank):
         s_host = torch.from_numpy(np.ascontiguousarray(s_loc)).pin_memory()
         out_pinned = torch.empty((f_total, m, m), dtype=torch.complex128).pin_memory()
         k_e2e = max(3, min(args.steps, 10))
+        path.drop_graph()                                      # the eager calls below allocate their own buffers: give the graph's pool back first
+        torch.cuda.synchronize()
+        torch.cuda.empty_cache()
         for _ in range(2):
             path.step(s_dev, want_x=False, gather=True)
         barrier()

@@ -1306,6 +1306,470 @@ __global__ void __launch_bounds__(NW * 32, MINB) sweep_left3_kernel(SweepParamsL
 }
 
 
+// ======================================================================================================================
+// Two points per CTA in anti-phase, warps specialised by SM sub-partition ("ping-pong").
+// Measured (tools/lat_bench.cu, profiles/r02_sweep_left_variants.md): hardware warp w issues on sub-partition w mod 4, and a scalar
+// FP64 instruction on a sub-partition whose FP64 pipe is fed DMMAs waits ~60 cycles for it (8.7 -> 69.6 cycles per dependent DFMA) --
+// that is the 2 k cycles of a pivot column step in the kernels above, where panel warps and DMMA warps share sub-partitions and
+// the two CTAs of an SM drift into opposite phases.  Here ONE 16-warp CTA per SM holds two points:
+//   P group: the 4 warps on sub-partition 0 -- panel factorisation, STORE, inverses, L~ (the code of the look-ahead body's panel warps);
+//   D group: the 12 warps on sub-partitions 1..3 -- LOAD + CHAIN of a block column (the code of the plain body), back substitution, outputs.
+// In half-step h the D group runs stage h/2 of point slot h mod 2 while the P group factors the panel the D group left in the other
+// slot one half-step earlier; a CTA barrier separates half-steps.  Stages of a point: 0 = load block column 0, j = 1 .. nb-1 = block
+// column j, nb = right-hand sides + back substitution + outputs; panel j follows stage j.  No scalar FP64 ever shares a pipe with a
+// DMMA stream of another warp, and the DMMA warps always have a column of the other point to work on.
+// ======================================================================================================================
+template <typename T, int NSTAGE>
+__global__ void __launch_bounds__(512, 1) sweep_left4_kernel(SweepParamsL<T> p, int R, int slot_smem) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int NW = 16, NP = 4, ND = 12, NTP = NP * 32, NTD = ND * 32;
+    constexpr int TPW = 3;                                       // 8-row tiles per D warp (R <= 256: 32 tiles over 12 warps)
+    constexpr int RBW = 2;                                       // 16-row blocks per D warp in the back substitution
+    constexpr int NC = 4;                                        // accumulator tiles per D warp: max(TPW, 2 RBW)
+    constexpr int SLP = 2;                                       // rows per P thread (R <= 256, 128 threads)
+    const int lane = threadIdx.x & 31, hw = threadIdx.x >> 5;
+    const bool isP = (hw & 3) == 0;
+    const int gw = isP ? (hw >> 2) : ((hw >> 2) * 3 + (hw & 3) - 1);   // warp index inside the group
+    const int gtid = gw * 32 + lane;
+    const int r = p.r, m = p.m;
+    const int g = lane >> 2, tl = lane & 3;
+    const int nb = R >> 4, ntiles = R >> 3, nper = nb + 1;
+    const int mct = (m + 7) >> 3;
+    T* ring = reinterpret_cast<T*>(smem_raw + 2 * (size_t)slot_smem);   // ND x NSTAGE x 128: FIFOs of the D warps, then 2 x 256: scratch of P warps 0, 1
+    T* ringw = isP ? ring + (size_t)ND * NSTAGE * 128 + (size_t)(gw & 1) * 256 : ring + (size_t)gw * NSTAGE * 128;
+    const bool hasA0 = p.A0 != nullptr, hasA1 = p.A1 != nullptr, hasA2 = p.A2 != nullptr;
+    FragOff fop;
+    {
+        const int sg = swz(g);
+        fop.g = g; fop.a0 = tl ^ sg; fop.a1 = (4 + tl) ^ sg; fop.c0 = (2 * tl) ^ sg; fop.c1 = (2 * tl + 1) ^ sg;
+        fop.b0 = tl * 16 + (g ^ swz(tl)); fop.b1 = (4 + tl) * 16 + (g ^ swz(4 + tl));
+    }
+    auto dsync = [&]() { asm volatile("bar.sync 2, %0;" :: "n"(NTD) : "memory"); };
+
+    // points of slot s: first_s + k stride
+    const long long stride = 2LL * gridDim.x;
+    long long npt0, npt1;
+    {
+        const long long f0 = 2LL * blockIdx.x, f1 = f0 + 1;
+        npt0 = f0 < p.F ? (p.F - f0 + stride - 1) / stride : 0;
+        npt1 = f1 < p.F ? (p.F - f1 + stride - 1) / stride : 0;
+    }
+    long long hend = 0;
+    if (npt0 > 0) hend = 2 * (npt0 * nper - 1) + 1;
+    if (npt1 > 0) { const long long e1 = 2 * (npt1 * nper - 1) + 2; hend = e1 > hend ? e1 : hend; }
+    for (int s = 0; s < 2; ++s) {
+        int* uf = reinterpret_cast<int*>(smem_raw + (size_t)s * slot_smem + sizeof(T) * ((size_t)R * 16 + 256 + 2 * NP * 8) + sizeof(CandKeyL) * 2 * NP) + R;
+        for (int i = threadIdx.x; i < (R >> 3); i += NW * 32) uf[i] = 0;
+    }
+    int epoch0 = 0, epoch1 = 0;
+    __syncthreads();
+
+    // MF_LEFT_TIMING (CTA 0): 0 = all half-steps, 1 = P group busy, 2 = D group busy in column stages, 3 = D in stage 0, 4 = D in the last stage,
+    // 5 = P busy in the first half of the panels (j < nb / 2), 6 = D busy in the first half of the columns
+    unsigned long long* tim = (p.timing && blockIdx.x == 0) ? p.timing : nullptr;
+    for (long long h = 0; h < hend; ++h) {
+        const long long t_h = tim ? clock64() : 0;
+        // ---- which slot, point and stage this group works on in this half-step ----
+        const int s = isP ? 1 - (int)(h & 1) : (int)(h & 1);
+        const long long q = isP ? (h - 1 - s) / 2 : (h >> 1);    // stage counter of the slot (P: the panel after D stage q)
+        const bool started = !isP || h >= 1 + s;
+        const long long k = started ? q / nper : 0;
+        const int js = started ? (int)(q - k * nper) : 0;
+        const long long npts = s ? npt1 : npt0;
+        const bool work = started && k < npts && (!isP || js < nb);
+        if (work) {
+            unsigned char* sbase = smem_raw + (size_t)s * slot_smem;
+            T* BC = reinterpret_cast<T*>(sbase);                 // R x 16: U blocks (fragment order) | panel rows (swizzled)
+            T* xch = BC + (size_t)R * 16;                        // 256
+            T* candrow = xch + 256;                              // 2 x NP x 8
+            CandKeyL* candk = reinterpret_cast<CandKeyL*>(candrow + 2 * NP * 8);
+            int* perm = reinterpret_cast<int*>(candk + 2 * NP);  // R
+            int* uflag = perm + R;                               // R / 8
+            int* lp = uflag + (R >> 3);                          // 16
+            int* info_sh = lp + 16;
+            T* Lg = p.ws + (2LL * blockIdx.x + s) * p.ws_stride;
+            T* Ug = Lg + (long long)nb * R * 16;
+            T* LIg = Ug + (long long)nb * nb * 256;
+            T* UIg = LIg + (long long)nb * 256;
+            const long long pt = 2LL * blockIdx.x + s + k * stride;
+
+            if (isP) {
+                // =============================== P group: panel js, STORE, inverses, L~ ===============================
+                const int j = js, tid = gtid, warp = gw;
+                T* PB = BC + (size_t)j * 256;
+                const int rows = R - 16 * j;
+#pragma unroll 1
+                for (int ip = 0; ip < 2; ++ip) {
+                    const int row0 = 8 * ip;
+                    int* pvl = lp + row0;
+                    if (rows - row0 > NTP) panel_factor_t<T, SLP, NP, NTP>(PB, 16, rows, row0, tid, candk, candrow, pvl, info_sh, 16 * j);
+                    else panel_factor_t<T, 1, NP, NTP>(PB, 16, rows, row0, tid, candk, candrow, pvl, info_sh, 16 * j);
+                    csync<NTP>();
+                    if (tid < row0) {                            // the exchanges also apply to the multipliers of the first inner panel
+                        const int c = tid, cbase = c & ~7, cin = c & 7;
+#pragma unroll
+                        for (int qq = 0; qq < 8; ++qq) {
+                            const int P = pvl[qq], Tg = row0 + qq;
+                            if (P != Tg) {
+                                T* x = PB + Tg * 16 + cbase + (cin ^ swz(qq));
+                                T* y = PB + P * 16 + cbase + (cin ^ swz(P & 7));
+                                const T tmp = *x; *x = *y; *y = tmp;
+                            }
+                        }
+                    }
+                    if (ip == 0) {
+                        if (tid < 8) stepb_column_t<T>(PB, 16, 0, 8 + tid, pvl);
+                        csync<NTP>();
+                        const int ntl = rows / 8 - 1;
+                        const T b0 = PB[8 + fop.b0], b1 = PB[8 + fop.b1];
+                        for (int ti = warp; ti < ntl; ti += NP) {
+                            T* rowp = PB + (8 * (1 + ti) + g) * 16;
+                            const T a0 = rowp[fop.a0], a1 = rowp[fop.a1];
+                            Acc<T> v;
+                            v.set(0, rowp[8 + fop.c0]); v.set(1, rowp[8 + fop.c1]);
+                            v.mma1(a0, b0); v.mma2(a0, b0);
+                            v.mma1(a1, b1); v.mma2(a1, b1);
+                            rowp[8 + fop.c0] = v.get(0); rowp[8 + fop.c1] = v.get(1);
+                        }
+                        csync<NTP>();
+                    }
+                }
+                csync<NTP>();
+                if (warp == 0) tri_inverse16<T, false>(PB, ringw, LIg + (long long)j * 256, xch, lane);
+                else if (warp == 1) tri_inverse16<T, true>(PB, ringw, UIg + (long long)j * 256, nullptr, lane);
+                if (tid == 64) {                                 // first lane of warp 2: the 16 exchanges of the panel applied to perm[]
+                    int lpr[16];
+#pragma unroll
+                    for (int c = 0; c < 16; ++c) lpr[c] = lp[c];
+#pragma unroll
+                    for (int c = 0; c < 16; ++c) { const int P = 16 * j + lpr[c]; const int tmp = perm[16 * j + c]; perm[16 * j + c] = perm[P]; perm[P] = tmp; }
+                }
+                csync<NTP>();
+                for (int e = tid; e < (rows - 16) * 16; e += NTP) {
+                    const int lr = 16 + (e >> 4), c = e & 15;
+                    const int o = perm[16 * j + lr];
+                    Lg[((long long)j * R + o) * 16 + c] = PB[mphys(lr, c, 16)];
+                }
+                for (int kq = warp; kq < j; kq += NP) {          // L~: rows of block j in the earlier panels, times L_jj^-1, in place
+                    T* Lk = Lg + (long long)kq * R * 16;
+                    T bq[4][2];
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk) {
+                        const T* rowp = Lk + (long long)perm[16 * j + 4 * kk + tl] * 16;
+                        bq[kk][0] = rowp[g]; bq[kk][1] = rowp[8 + g];
+                    }
+#pragma unroll
+                    for (int hh = 0; hh < 2; ++hh) {
+                        Acc<T> d0, d1;
+                        d0.zero(); d1.zero();
+#pragma unroll
+                        for (int kk = 0; kk < 4; ++kk) {
+                            if (kk < 2 || hh == 1) {
+                                const T a = xch[((hh * 4 + kk) << 5) + lane];
+                                d0.mma1(a, bq[kk][0]); d1.mma1(a, bq[kk][1]);
+                                d0.mma2(a, bq[kk][0]); d1.mma2(a, bq[kk][1]);
+                            }
+                        }
+                        T* rowp = Lk + (long long)perm[16 * j + 8 * hh + g] * 16 + 2 * tl;
+                        rowp[0] = d0.get(0); rowp[1] = d0.get(1);
+                        rowp[8] = d1.get(0); rowp[9] = d1.get(1);
+                    }
+                }
+            } else {
+                // =============================== D group: stage js of the point ===============================
+                const int warp = gw, tid = gtid;
+                const double c0 = p.c0[pt], c1 = p.c1[pt], c2 = p.c2[pt], cb = p.cb[pt];
+                const bool isrhs = (js == nb);
+                const int j = js;
+                auto elem = [&](const int o, const int cl) -> T {
+                    if (isrhs) {
+                        const bool in = (o < r) & (cl < m);
+                        const T x = __ldg(p.Br + (in ? (long long)o * p.ldb + cl : 0));
+                        return in ? Num<T>::scale(cb, x) : Num<T>::zero();
+                    }
+                    const int cg = 16 * j + cl;
+                    const bool in = (o < r) & (cg < r);
+                    const long long off = in ? (long long)o * p.lda + cg : 0;
+                    T v = Num<T>::zero();
+                    if (hasA0) v = Num<T>::scale(c0, __ldg(p.A0 + off));
+                    if (hasA1) Num<T>::axpy(v, c1, __ldg(p.A1 + off));
+                    if (hasA2) Num<T>::axpy(v, c2, __ldg(p.A2 + off));
+                    return in ? v : ((o == cg) ? Num<T>::one() : Num<T>::zero());
+                };
+                const int imax = min(TPW, max(0, (ntiles - warp + ND - 1) / ND));   // owned tiles: t = warp + ND i
+                if (js == 0) {
+                    // ---- a new point: identity permutation, block column 0 straight to the panel buffer ----
+                    for (int i = tid; i < R; i += NTD) perm[i] = i;
+                    if (tid == 0) *info_sh = 0;
+#pragma unroll
+                    for (int i = 0; i < TPW; ++i) {
+                        const int t = warp + ND * i;
+                        if (i < imax) {
+                            const int o = 8 * t + g;
+#pragma unroll
+                            for (int ct = 0; ct < 2; ++ct)
+#pragma unroll
+                                for (int e = 0; e < 2; ++e) BC[mphys(8 * t + g, 8 * ct + 2 * tl + e, 16)] = elem(o, 8 * ct + 2 * tl + e);
+                        }
+                    }
+                } else {
+                    const int nct = isrhs ? mct : 2;
+                    const int epoch = s ? ++epoch1 : ++epoch0;
+                    Acc<T> C[NC][2];
+                    // ---- LOAD ----
+                    int obase[TPW];
+#pragma unroll
+                    for (int i = 0; i < TPW; ++i) {
+                        const int t = warp + ND * i;
+                        obase[i] = 0;
+                        C[i][0].zero(); C[i][1].zero();
+                        if (i < imax) {
+                            const int o = perm[8 * t + g];
+                            obase[i] = o * 16 + tl;
+                            if (t >= 2 * j) {
+#pragma unroll
+                                for (int ct = 0; ct < 2; ++ct)
+#pragma unroll
+                                    for (int e = 0; e < 2; ++e) C[i][ct].set(e, elem(o, 8 * ct + 2 * tl + e));
+                            } else {                             // rows of a finished block b: L_bb^-1 A[b, j]
+                                const int b = t >> 1, hh = t & 1;
+                                const T* li = LIg + (long long)b * 256 + ((hh * 4) << 5) + lane;
+#pragma unroll
+                                for (int kk = 0; kk < 4; ++kk) {
+                                    if (kk < 2 || hh == 1) {
+                                        const T a = li[kk << 5];
+                                        const int ok = perm[16 * b + 4 * kk + tl];
+                                        const T b0 = elem(ok, g), b1 = elem(ok, 8 + g);
+                                        C[i][0].mma1(a, b0); if (nct > 1) C[i][1].mma1(a, b1);
+                                        C[i][0].mma2(a, b0); if (nct > 1) C[i][1].mma2(a, b1);
+                                    }
+                                }
+                            }
+                        }
+                    }
+                    auto publish = [&](const Acc<T> (&Ct)[2], const int t) {
+                        const int b = t >> 1, hh = t & 1;
+                        T* slot = BC + b * 256;
+#pragma unroll
+                        for (int ct = 0; ct < 2; ++ct)
+#pragma unroll
+                            for (int e = 0; e < 2; ++e) slot[bfrag_off(8 * hh + g, 8 * ct + 2 * tl + e)] = Ct[ct].get(e);
+                        if (!isrhs) {
+                            T* ub = Ug + ((long long)b * nb + j) * 256;
+#pragma unroll
+                            for (int ct = 0; ct < 2; ++ct) {
+                                T* dst = ub + afrag_off(8 * hh + g, 8 * ct + 2 * tl);
+                                dst[0] = Ct[ct].get(0); dst[1] = Ct[ct].get(1);
+                            }
+                        }
+                        __syncwarp();
+                        __threadfence_block();
+                        if (lane == 0) *reinterpret_cast<volatile int*>(uflag + t) = epoch;
+                    };
+                    // ---- CHAIN ----
+                    {
+                        auto i0 = [&](const int kq) { const int d = 2 * (kq + 1) - warp; return d <= 0 ? 0 : (d + ND - 1) / ND; };
+                        int pk = 0, pi = i0(0);
+                        auto pnorm = [&]() { while (pk < j && pi >= imax) { ++pk; pi = i0(pk); } };
+                        auto issue = [&](const int stage) {
+                            int ob = obase[0];
+#pragma unroll
+                            for (int i = 1; i < TPW; ++i) ob = (pi == i) ? obase[i] : ob;
+                            const T* src = Lg + (long long)pk * R * 16 + ob;
+                            T* dst = ringw + stage * 128 + lane;
+#pragma unroll
+                            for (int kk = 0; kk < 4; ++kk) Num<T>::cp_async(dst + 32 * kk, src + 4 * kk);
+                        };
+                        pnorm();
+                        int pstage = 0, cstage = 0;
+#pragma unroll
+                        for (int st = 0; st < NSTAGE - 1; ++st) {
+                            if (pk < j) { issue(pstage); ++pi; pnorm(); }
+                            cpa_commit();
+                            pstage = (pstage + 1 == NSTAGE) ? 0 : pstage + 1;
+                        }
+#pragma unroll
+                        for (int i = 0; i < TPW; ++i)            // block 0 needs no update
+                            if (i < imax && warp + ND * i < 2) publish(C[i], warp + ND * i);
+#pragma unroll 1
+                        for (int kq = 0; kq < j; ++kq) {
+                            const int ifirst = i0(kq);
+                            if (ifirst >= imax) continue;
+                            {
+                                volatile int* f = uflag + 2 * kq;
+                                while (f[0] != epoch || f[1] != epoch) { __nanosleep(20); }
+                                __threadfence_block();
+                            }
+                            const T* Uk = BC + kq * 256 + lane;
+#pragma unroll
+                            for (int i = 0; i < TPW; ++i) {
+                                if (i >= ifirst && i < imax) {
+                                    if (pk < j) { issue(pstage); ++pi; pnorm(); }
+                                    cpa_commit();
+                                    pstage = (pstage + 1 == NSTAGE) ? 0 : pstage + 1;
+                                    cpa_wait<NSTAGE - 1>();
+                                    const T* af = ringw + cstage * 128 + lane;
+                                    cstage = (cstage + 1 == NSTAGE) ? 0 : cstage + 1;
+#pragma unroll
+                                    for (int kk = 0; kk < 4; ++kk) {
+                                        const T a = af[32 * kk];
+                                        const T b0 = Uk[(kk * 2) << 5], b1 = Uk[(kk * 2 + 1) << 5];
+                                        C[i][0].mma1(a, b0); if (nct > 1) C[i][1].mma1(a, b1);
+                                        C[i][0].mma2(a, b0); if (nct > 1) C[i][1].mma2(a, b1);
+                                    }
+                                    const int t = warp + ND * i;
+                                    if ((t >> 1) == kq + 1 && kq + 1 < j) publish(C[i], t);
+                                }
+                            }
+                        }
+                        cpa_wait<0>();
+                    }
+                    if (!isrhs) {
+                        // ---- rows at positions >= 16 j -> the panel buffer (swizzled); the P group factors it in the next half-step ----
+                        T* PB = BC + (size_t)j * 256;
+#pragma unroll
+                        for (int i = 0; i < TPW; ++i) {
+                            const int t = warp + ND * i;
+                            if (i < imax && t >= 2 * j) {
+#pragma unroll
+                                for (int ct = 0; ct < 2; ++ct)
+#pragma unroll
+                                    for (int e = 0; e < 2; ++e) PB[mphys(8 * (t - 2 * j) + g, 8 * ct + 2 * tl + e, 16)] = C[i][ct].get(e);
+                            }
+                        }
+                    } else {
+                        // ---- every U row of the right-hand sides is published by now: back substitution and outputs ----
+                        dsync();
+                        for (int e = tid; e < nb * 256 * (int)sizeof(T) / 128; e += NTD)
+                            asm volatile("prefetch.global.L2 [%0];" :: "l"(UIg + (size_t)e * (128 / sizeof(T))));
+#pragma unroll
+                        for (int bi = 0; bi < RBW; ++bi) {
+                            const int b = warp + bi * ND;
+#pragma unroll
+                            for (int hh = 0; hh < 2; ++hh)
+#pragma unroll
+                                for (int ct = 0; ct < 2; ++ct)
+#pragma unroll
+                                    for (int e = 0; e < 2; ++e)
+                                        C[2 * bi + hh][ct].set(e, b < nb ? BC[b * 256 + bfrag_off(8 * hh + g, 8 * ct + 2 * tl + e)] : Num<T>::zero());
+                        }
+                        auto l2_prefetch_u = [&](const int kq) {
+                            if (kq < 1) return;
+                            constexpr int LPB = 256 * (int)sizeof(T) / 128;
+                            for (int e = tid; e < kq * LPB; e += NTD) {
+                                const int b = e / LPB, ln = e - b * LPB;
+                                asm volatile("prefetch.global.L2 [%0];" :: "l"(Ug + ((long long)b * nb + kq) * 256 + (size_t)ln * (128 / sizeof(T))));
+                            }
+                        };
+                        l2_prefetch_u(nb - 1);
+                        l2_prefetch_u(nb - 2);
+                        int pk = nb - 1, pbi = 0, ph = 0;
+                        auto pnorm = [&]() { while (pk >= 1 && (pbi >= RBW || warp + pbi * ND >= pk)) { --pk; pbi = 0; } };
+                        auto issue = [&](const int stage) {
+                            const T* src = Ug + ((long long)(warp + pbi * ND) * nb + pk) * 256 + ph * 128 + lane;
+                            T* dst = ringw + stage * 128 + lane;
+#pragma unroll
+                            for (int kk = 0; kk < 4; ++kk) Num<T>::cp_async(dst + 32 * kk, src + 32 * kk);
+                        };
+                        auto pnext = [&]() { ph ^= 1; if (ph == 0) ++pbi; pnorm(); };
+                        pnorm();
+                        int pstage = 0, cstage = 0;
+#pragma unroll
+                        for (int st = 0; st < NSTAGE - 1; ++st) {
+                            if (pk >= 1) { issue(pstage); pnext(); }
+                            cpa_commit();
+                            pstage = (pstage + 1 == NSTAGE) ? 0 : pstage + 1;
+                        }
+                        dsync();
+                        for (int kq = nb - 1; kq >= 0; --kq) {
+#pragma unroll
+                            for (int bi = 0; bi < RBW; ++bi) {
+                                if (warp + bi * ND == kq) {      // x_k = U_kk^-1 times the finished block
+#pragma unroll
+                                    for (int hh = 0; hh < 2; ++hh)
+#pragma unroll
+                                        for (int ct = 0; ct < 2; ++ct)
+#pragma unroll
+                                            for (int e = 0; e < 2; ++e) xch[bfrag_off(8 * hh + g, 8 * ct + 2 * tl + e)] = C[2 * bi + hh][ct].get(e);
+                                    __syncwarp();
+                                    const T* ui = UIg + (long long)kq * 256 + lane;
+                                    T* slot = BC + kq * 256;
+#pragma unroll
+                                    for (int hh = 0; hh < 2; ++hh) {
+                                        Acc<T> d0, d1;
+                                        d0.zero(); d1.zero();
+#pragma unroll
+                                        for (int kk = 0; kk < 4; ++kk) {
+                                            if (hh == 0 || kk >= 2) {
+                                                const T a = ui[(hh * 4 + kk) << 5];
+                                                const T b0 = xch[((kk * 2) << 5) + lane], b1 = xch[((kk * 2 + 1) << 5) + lane];
+                                                d0.mma1(a, b0); if (mct > 1) d1.mma1(a, b1);
+                                                d0.mma2(a, b0); if (mct > 1) d1.mma2(a, b1);
+                                            }
+                                        }
+#pragma unroll
+                                        for (int e = 0; e < 2; ++e) {
+                                            slot[bfrag_off(8 * hh + g, 2 * tl + e)] = d0.get(e);
+                                            slot[bfrag_off(8 * hh + g, 8 + 2 * tl + e)] = d1.get(e);
+                                        }
+                                    }
+                                }
+                            }
+                            dsync();
+                            l2_prefetch_u(kq - 2);
+                            const T* Xk = BC + kq * 256 + lane;
+#pragma unroll
+                            for (int bi = 0; bi < RBW; ++bi) {
+                                const int b = warp + bi * ND;
+                                if (b < kq) {
+#pragma unroll
+                                    for (int hh = 0; hh < 2; ++hh) {
+                                        if (pk >= 1) { issue(pstage); pnext(); }
+                                        cpa_commit();
+                                        pstage = (pstage + 1 == NSTAGE) ? 0 : pstage + 1;
+                                        cpa_wait<NSTAGE - 1>();
+                                        const T* af = ringw + cstage * 128 + lane;
+                                        cstage = (cstage + 1 == NSTAGE) ? 0 : cstage + 1;
+#pragma unroll
+                                        for (int kk = 0; kk < 4; ++kk) {
+                                            const T a = Num<T>::neg(af[32 * kk]);
+                                            const T b0 = Xk[(kk * 2) << 5], b1 = Xk[(kk * 2 + 1) << 5];
+                                            C[2 * bi + hh][0].mma1(a, b0); if (mct > 1) C[2 * bi + hh][1].mma1(a, b1);
+                                            C[2 * bi + hh][0].mma2(a, b0); if (mct > 1) C[2 * bi + hh][1].mma2(a, b1);
+                                        }
+                                    }
+                                }
+                            }
+                        }
+                        cpa_wait<0>();
+                        dsync();
+                        auto xs = [&](const int i, const int c) -> T { return BC[(i >> 4) * 256 + bfrag_off(i & 15, c)]; };
+                        if (p.X) for (int e = tid; e < r * m; e += NTD) { const int i = e / m, c = e - i * m; p.X[pt * (long long)r * m + e] = xs(i, c); }
+                        if (p.info && tid == 0) p.info[pt] = *info_sh;
+                        if (p.S) {
+                            for (int e = warp; e < m * m; e += ND) {
+                                const int a = e / m, b = e - a * m;
+                                T acc = Num<T>::zero();
+                                for (int kq = lane; kq < r; kq += 32) Num<T>::fma_(acc, xs(kq, a), Num<T>::scale(cb, __ldg(p.Br + (long long)kq * p.ldb + b)));
+                                acc = warp_sum(acc);
+                                if (lane == 0) p.S[pt * (long long)m * m + e] = Num<T>::jz(p.zs[pt], acc);
+                            }
+                        }
+                    }
+                }
+            }
+            if (tim && gtid == 0) {
+                const unsigned long long dt = (unsigned long long)(clock64() - t_h);
+                if (isP) { atomicAdd(tim + 1, dt); if (js < nb / 2) atomicAdd(tim + 5, dt); }
+                else { atomicAdd(tim + (js == 0 ? 3 : (js == nb ? 4 : 2)), dt); if (js > 0 && js <= nb / 2) atomicAdd(tim + 6, dt); }
+            }
+        }
+        __syncthreads();
+        if (tim && threadIdx.x == 0) atomicAdd(tim, (unsigned long long)(clock64() - t_h));
+    }
+}
+
+
 struct LeftGeom { int R, nb, NW, RBW, MINB; size_t smem, slot_elems; int cfg; };
 
 // Geometry per size (cfg): warps per CTA x owned 16-row blocks per warp must cover R / 16 blocks.
@@ -1323,13 +1787,17 @@ LeftGeom left_geom(int r, int m) {
     if (sizeof(T) == 16) cfg = gm.nb <= 7 ? 1 : (gm.nb <= 16 ? 2 : 3);
     else cfg = gm.nb <= 8 ? 1 : (gm.nb <= 12 ? 5 : (gm.nb <= 16 ? 2 : 4));
     const int cfg_auto = cfg;
-    if (const char* e = getenv("MF_LEFT_CFG")) { const int c = atoi(e); if (c >= 1 && c <= (sizeof(T) == 8 ? 5 : 4)) cfg = c; }
+    if (const char* e = getenv("MF_LEFT_CFG")) {
+        const int c = atoi(e);
+        if ((c >= 1 && c <= (sizeof(T) == 8 ? 5 : 4)) || (c == 8 && sizeof(T) == 16 && gm.nb >= 2 && gm.nb <= 16)) cfg = c;
+    }
     auto shape = [&](int c) {
         switch (c) {
             case 1:  gm.NW = 4; gm.RBW = 2; break;
             case 2:  gm.NW = 8; gm.RBW = 2; break;
             case 3:  gm.NW = 16; gm.RBW = 2; break;
             case 5:  gm.NW = 4; gm.RBW = 4; break;                // float64 only: four 4-warp CTAs per SM up to R = 256
+            case 8:  gm.NW = 16; gm.RBW = 2; break;               // complex128, R <= 256: one 16-warp CTA, two points in anti-phase (sweep_left4_kernel)
             default: gm.NW = 8; gm.RBW = 4; break;
         }
     };
@@ -1408,6 +1876,42 @@ int launch_left(SweepParamsL<T> p, const LeftGeom& gm, size_t ws_bytes, cudaStre
     return 0;
 }
 
+// the two-points-per-CTA kernel: one CTA per SM, two workspace slots and two shared-memory point slots each
+template <typename T>
+int launch_left4(SweepParamsL<T> p, const LeftGeom& gm, size_t ws_bytes, cudaStream_t stream) {
+    constexpr int NSTAGE = 3, NP = 4;
+    size_t slot_smem = sizeof(T) * ((size_t)gm.R * 16 + 256 + 2 * NP * 8) + sizeof(CandKeyL) * 2 * NP + sizeof(int) * ((size_t)gm.R + (size_t)gm.R / 8 + 16 + 4);
+    slot_smem = (slot_smem + 127) / 128 * 128;
+    const size_t smem = 2 * slot_smem + sizeof(T) * (12 * NSTAGE * 128 + 2 * 256);
+    if (smem > 227 * 1024) MF_FAIL_ARG(7, "two-point left-looking sweep does not fit in shared memory for this r");
+    auto kern = sweep_left4_kernel<T, NSTAGE>;
+    MF_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const size_t slot = sizeof(T) * gm.slot_elems;
+    long long grid = mf_num_sms();
+    if (2 * grid > p.F) grid = (p.F + 1) / 2;
+    if ((long long)(ws_bytes / slot) / 2 < grid) grid = (long long)(ws_bytes / slot) / 2;
+    if (grid < 1 || !p.ws) MF_FAIL_ARG(21, "workspace too small for the left-looking blocked sweep (see mf_sweep_ws_bytes)");
+    p.ws_stride = (long long)gm.slot_elems;
+    p.timing = nullptr;
+    p.remap = 0;
+    static const bool want_timing = getenv("MF_LEFT_TIMING") != nullptr;
+    if (want_timing) { MF_CHECK_CUDA(cudaMalloc(&p.timing, 16 * sizeof(unsigned long long))); MF_CHECK_CUDA(cudaMemsetAsync(p.timing, 0, 16 * 8, stream)); }
+    kern<<<(unsigned)grid, 512, smem, stream>>>(p, gm.R, (int)slot_smem);
+    MF_CHECK_LAUNCH();
+    if (want_timing) {
+        unsigned long long h[16];
+        MF_CHECK_CUDA(cudaMemcpyAsync(h, p.timing, sizeof(h), cudaMemcpyDeviceToHost, stream));
+        MF_CHECK_CUDA(cudaStreamSynchronize(stream));
+        cudaFree(p.timing);
+        const double pairs = (double)((p.F + 2 * grid - 1) / (2 * grid));
+        fprintf(stderr, "[MF_LEFT_TIMING] two-point CTA r=%d m=%d grid=%lld  cycles per point pair: all half-steps %.0f | P busy %.0f (first half of the panels %.0f) | "
+                        "D busy: columns %.0f (first half %.0f), stage 0 %.0f, last stage %.0f\n", p.r, p.m, grid, h[0] / pairs, h[1] / pairs, h[5] / pairs,
+                h[2] / pairs, h[6] / pairs, h[3] / pairs, h[4] / pairs);
+    }
+    if (p.S) return gsm_finish_launch(p.S, p.m, p.F, stream);
+    return 0;
+}
+
 template <typename T>
 int dispatch_left(const SweepParamsL<T>& p, size_t ws_bytes, cudaStream_t stream) {
     const LeftGeom gm = left_geom<T>(p.r, p.m);
@@ -1417,6 +1921,9 @@ int dispatch_left(const SweepParamsL<T>& p, size_t ws_bytes, cudaStream_t stream
         case 2:  return launch_left<T, 8, 2, REAL ? 3 : 2>(p, gm, ws_bytes, stream);
         case 3:  return launch_left<T, 16, 2, 1>(p, gm, ws_bytes, stream);
         case 5:  return launch_left<T, 4, 4, REAL ? 4 : 1>(p, gm, ws_bytes, stream);
+        case 8:
+            if constexpr (!REAL) return launch_left4<T>(p, gm, ws_bytes, stream);
+            return launch_left<T, 8, 2, 3>(p, gm, ws_bytes, stream);
         default: return launch_left<T, 8, 4, REAL ? 2 : 1>(p, gm, ws_bytes, stream);
     }
 }
@@ -1433,7 +1940,7 @@ size_t left_ws_bytes(int r, int m, long long F) {
     const LeftGeom gm = left_geom<T>(r, m);
     // resident CTAs per SM of the geometry (the __launch_bounds__ the kernels are built with; the launcher clamps its grid to the slots it is given)
     constexpr bool REAL = sizeof(T) == 8;
-    const int per_sm = gm.cfg == 1 ? 4 : gm.cfg == 2 ? (REAL ? 3 : 2) : gm.cfg == 3 ? 1 : gm.cfg == 5 ? 4 : (REAL ? 2 : 1);
+    const int per_sm = gm.cfg == 1 ? 4 : gm.cfg == 2 ? (REAL ? 3 : 2) : gm.cfg == 3 ? 1 : gm.cfg == 8 ? 2 : gm.cfg == 5 ? 4 : (REAL ? 2 : 1);
     long long grid = (long long)mf_num_sms() * per_sm; if (grid > F) grid = F; if (grid < 1) grid = 1;
     return sizeof(T) * gm.slot_elems * (size_t)grid;
 }
