@@ -121,6 +121,17 @@ def _real_inputs(*arrs) -> bool:
 
 
 # ------------------------------------------------------------------------------- device model (hot stages)
+def _device_tensors(obj):
+    """The CUDA tensors held by a device operand record (DeviceCSR / DeviceCSC, including the row-grouped arrays)."""
+    import torch
+    out = []
+    for v in vars(obj).values():
+        for t in (v if isinstance(v, tuple) else (v,)):
+            if isinstance(t, torch.Tensor) and t.is_cuda:
+                out.append(t)
+    return out
+
+
 class _DeviceOperators:
     """Full-order operators uploaded once: CSR views for the SpMMs, CSC port matrix."""
 
@@ -171,8 +182,13 @@ class _DeviceOperators:
         all of them (no-op once waited for, or without a side stream)."""
         import torch
         keys = list(self._ready) if key is None else ([key] if key in self._ready else [])
+        cur = torch.cuda.current_stream()
         for k in keys:
-            torch.cuda.current_stream().wait_event(self._ready.pop(k))
+            cur.wait_event(self._ready.pop(k))
+            # the operand was allocated on the upload stream and is consumed on this one: tell the caching allocator
+            obj = self.b if k == "b" else self.at[k]
+            for t in _device_tensors(obj):
+                t.record_stream(cur)
 
     def a_csr(self, i):
         if self._a[i] is None and not self.zero[i]:
@@ -450,12 +466,12 @@ def new_solution_for_projection_base(md: ModelDefinition, q, opm=None, time_stat
     return solve_fem_point(md.domain[idx_max], md), error
 
 
-def projection_base(md: ModelDefinition, _return_device: bool = False):
+def projection_base(md: ModelDefinition, _return_device: bool = False, _ops: Optional[_DeviceOperators] = None):
     """Greedy basis construction (implementation.py:217-328): start from the two end points of the domain, add
     the full-order solution at the arg-max of the residual estimator until it drops below ERROR_THRESHOLD,
     re-orthonormalising ``[q | q_new]`` each time (:297-298)."""
     from . import device as dv
-    ops = _DeviceOperators(md)
+    ops = _ops or _DeviceOperators(md)            # a caller that projects afterwards passes its own (one upload per call)
     initial_vectors = np.hstack((solve_fem_point(md.domain[0], md), solve_fem_point(md.domain[-1], md)))
     if USE_OPM:                                   # incremental search: implementation.py:230-263 (set-up), :275-295 (growth)
         state = _GreedyState(md, ops, initial_vectors)
@@ -601,13 +617,13 @@ def morfem(domain: np.ndarray, a0: csc_array, a1: csc_array, a2: csc_array, b: c
     import torch
     md = ModelDefinition(domain, a0, a1, a2, b, t_a0, t_a1, t_a2, t_b)
     start = time.time()
+    ops = _DeviceOperators(md)                                                      # uploaded once: greedy search and projection share it
     if USE_EQUALLY_DISTRIBUTED:
         qd = _block_to_device(projection_base_equally_distributed(md), md)
     else:
-        qd = projection_base(md, _return_device=True)
+        qd = projection_base(md, _return_device=True, _ops=ops)
     if VERBOSE:
         print("Projection base: ", time.time() - start, " s")
-    ops = _DeviceOperators(md)
     a0_r, a1_r, a2_r, b_r = ops.project(qd)                                         # :178-184
     res = _sweep_device(domain, [a0_r, a1_r, a2_r], b_r, t_a0, t_a1, t_a2, t_b, want_x=True, want_gsm=False)  # :186
     _warn_singular(res.info.cpu().numpy())

@@ -102,11 +102,11 @@ def finite_element_method_model_order_reduction_gsm(frequency_points, gate_count
     md = ModelDefinition(frequency_points, in_c, in_a1, in_gamma, in_b, lambda t: 1., lambda t: t, lambda t: t ** 2,
                          lambda t: b_coefficient(t))
     start = time.time()
+    ops = impl._DeviceOperators(md)                              # uploaded once: greedy search and projection share it
     if impl.USE_EQUALLY_DISTRIBUTED:
         qd = impl._block_to_device(impl.projection_base_equally_distributed(md), md)
     else:
-        qd = impl.projection_base(md, _return_device=True)
-    ops = impl._DeviceOperators(md)
+        qd = impl.projection_base(md, _return_device=True, _ops=ops)
     a0_r, a1_r, a2_r, b_r = ops.project(qd)
     res = impl._sweep_device(frequency_points, [a0_r, a1_r, a2_r], b_r, md.t_a0, md.t_a1, md.t_a2, md.t_b,
                              want_x=return_details, want_gsm=True)

@@ -157,6 +157,40 @@ def test_sweep_singular_and_pivoting_in_the_streamed_kernel(dv):
         assert list(res.info.cpu().numpy()) == [78, 78, 78], variant
 
 
+@pytest.mark.parametrize("r,m,nf", [(40, 3, 7), (130, 5, 301), (256, 4, 297), (250, 8, 2)])
+def test_two_point_cta_kernel_matches_oracle(dv, r, m, nf, monkeypatch):
+    """sweep_left4_kernel (MF_LEFT_CFG=8: two points per CTA in anti-phase, panel warps and DMMA warps on different SM
+    sub-partitions) against the oracle: odd point counts (the second slot of a CTA runs out first), a single CTA, row exchanges in
+    every panel and the report of an exactly singular point."""
+    from morfem_b200 import synthetic
+    monkeypatch.setenv("MF_LEFT_CFG", "8")
+    a0, a1, a2, b = synthetic.reduced_model(r, m, seed=300 + r)
+    f = np.linspace(3e9, 5e9, nf)
+    tb = orc.b_coefficient
+    x_ref = orc.reduced_sweep(f, a0, a1, a2, b, lambda t: 1.0, lambda t: t, lambda t: t ** 2, tb)
+    s_ref = orc.scattering_sweep(f, x_ref, b)
+    cond = np.array([np.linalg.cond(orc.system_matrix(1.0, t, t ** 2, a0, a1, a2)) for t in f])
+    cb = np.array([tb(t) for t in f])
+    tol = np.maximum(1e-10, 20 * EPS * cond)
+    res = run_sweep(dv, f, a0, a1, a2, b, cb, variant=5)
+    assert not np.any(res.info.cpu().numpy())
+    assert np.all(per_point_rel(res.x.cpu().numpy().real, x_ref) < tol)
+    assert np.all(per_point_rel(res.gsm.cpu().numpy(), s_ref) < tol)
+    # a permutation-like matrix (exchanges in every panel) and an exactly singular one
+    rng = np.random.default_rng(r)
+    p0 = np.fliplr(np.eye(r)) * 2.0 + 1e-3 * rng.standard_normal((r, r))
+    p0 = (p0 + p0.T) / 2
+    f3 = np.array([3e9, 4e9, 5e9])
+    zero = np.zeros((r, r))
+    xp = orc.reduced_sweep(f3, p0, zero, zero, b, lambda t: 1.0, lambda t: t, lambda t: t ** 2, lambda t: 1.0)
+    res = run_sweep(dv, f3, p0, None, None, b, np.ones(3), variant=5)
+    assert np.all(per_point_rel(res.x.cpu().numpy().real, xp) < 1e-11)
+    sing = np.eye(r)
+    sing[r // 2 + 3, r // 2 + 3] = 0.0
+    res = run_sweep(dv, f3, sing, None, None, np.ones((r, m)), np.ones(3), variant=5, want_gsm=False)
+    assert list(res.info.cpu().numpy()) == [r // 2 + 4] * 3
+
+
 def test_sweep_outputs_are_optional_and_idempotent(dv):
     from morfem_b200 import synthetic
     r, m, nf = 24, 2, 50
