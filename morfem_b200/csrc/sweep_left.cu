@@ -49,9 +49,27 @@ template <> struct Num<double> {
     static __device__ __forceinline__ double ldsv(unsigned addr) {
         double v; asm volatile("ld.volatile.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr)); return v;
     }
-    static __device__ __forceinline__ void cp_async(void* dst, const void* src) {
+    static __device__ __forceinline__ void cp16(void* dst, const void* src) {
         const unsigned s = (unsigned)__cvta_generic_to_shared(dst);
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" :: "r"(s), "l"(src) : "memory");
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" :: "r"(s), "l"(src) : "memory");
+    }
+    // One FIFO stage (a 8 x 16 A operand in fragment order: element (g, 4 kk + t) at 32 kk + 4 g + t) from 8 matrix rows of 16 elements;
+    // `src_tl` = row of this lane's g, plus t.  Two 16-byte copies per lane (pairs of neighbouring columns): the 8-byte cp.async this
+    // replaces cost four shared-memory wavefronts per instruction -- 40 % of all shared-memory wavefronts of the float64 kernel
+    // (profiles/r02_sweep_left_f64_ncu.md).
+    static __device__ __forceinline__ void fifo_rows(double* stage, const double* src_tl, const int lane) {
+        const int g = lane >> 2, t = lane & 3;
+        const double* row = src_tl - t;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            const int kk = 2 * c + (t >> 1), tp = t & 1;
+            cp16(stage + 32 * kk + 4 * g + 2 * tp, row + 4 * kk + 2 * tp);
+        }
+    }
+    // One FIFO stage from 128 elements that are already in fragment order in global memory
+    static __device__ __forceinline__ void fifo_flat(double* stage, const double* src, const int lane) {
+#pragma unroll
+        for (int c = 0; c < 2; ++c) cp16(stage + 64 * c + 2 * lane, src + 64 * c + 2 * lane);
     }
     // j zs acc  (the impedance matrix is purely imaginary for a real model)
     static __device__ __forceinline__ cplx jz(double zs, double acc) { return cmake(0.0, zs * acc); }
@@ -78,6 +96,14 @@ template <> struct Num<cplx> {
     static __device__ __forceinline__ void cp_async(void* dst, const void* src) {
         const unsigned s = (unsigned)__cvta_generic_to_shared(dst);
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" :: "r"(s), "l"(src) : "memory");
+    }
+    static __device__ __forceinline__ void fifo_rows(cplx* stage, const cplx* src_tl, const int lane) {
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) cp_async(stage + 32 * kk + lane, src_tl + 4 * kk);
+    }
+    static __device__ __forceinline__ void fifo_flat(cplx* stage, const cplx* src, const int lane) {
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) cp_async(stage + 32 * kk + lane, src + 32 * kk + lane);
     }
     static __device__ __forceinline__ cplx jz(double zs, cplx acc) { return cmake(-zs * acc.y, zs * acc.x); }
 };
@@ -541,9 +567,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) sweep_left2_kernel(SweepParamsL
 #pragma unroll
                     for (int i = 1; i < TPW; ++i) ob = (pi == i) ? obase[i] : ob;
                     const T* src = Lg + (long long)pk * R * 16 + ob;
-                    T* dst = ringw + stage * 128 + lane;
-#pragma unroll
-                    for (int kk = 0; kk < 4; ++kk) Num<T>::cp_async(dst + 32 * kk, src + 4 * kk);
+                    Num<T>::fifo_rows(ringw + stage * 128, src, lane);
                 };
                 pnorm();
                 int pstage = 0, cstage = 0;
@@ -1055,9 +1079,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) sweep_left3_kernel(SweepParamsL
                 auto issue = [&](const int stage) {
                     const int o = perm[8 * ptile + g];
                     const T* src = Lg + ((long long)pk * R + o) * 16 + tl;
-                    T* dst = ringw + stage * 128 + lane;
-#pragma unroll
-                    for (int kk = 0; kk < 4; ++kk) Num<T>::cp_async(dst + 32 * kk, src + 4 * kk);
+                    Num<T>::fifo_rows(ringw + stage * 128, src, lane);
                 };
                 pnorm();
                 int pstage = 0, cstage = 0;
@@ -1124,9 +1146,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) sweep_left3_kernel(SweepParamsL
 #pragma unroll
                     for (int i = 1; i < TPW; ++i) ob = (pi == i) ? obase[i] : ob;
                     const T* src = Lg + (long long)pk * R * 16 + ob;
-                    T* dst = ringw + stage * 128 + lane;
-#pragma unroll
-                    for (int kk = 0; kk < 4; ++kk) Num<T>::cp_async(dst + 32 * kk, src + 4 * kk);
+                    Num<T>::fifo_rows(ringw + stage * 128, src, lane);
                 };
                 pnorm();
                 int pstage = 0, cstage = 0;
@@ -1209,10 +1229,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) sweep_left3_kernel(SweepParamsL
             int pk = nb - 1, pbi = 0, ph = 0;
             auto pnorm = [&]() { while (pk >= 1 && (pbi >= RBW || warp + pbi * NW >= pk)) { --pk; pbi = 0; } };
             auto issue = [&](const int stage) {
-                const T* src = Ug + ((long long)(warp + pbi * NW) * nb + pk) * 256 + ph * 128 + lane;
-                T* dst = ringw + stage * 128 + lane;
-#pragma unroll
-                for (int kk = 0; kk < 4; ++kk) Num<T>::cp_async(dst + 32 * kk, src + 32 * kk);
+                Num<T>::fifo_flat(ringw + stage * 128, Ug + ((long long)(warp + pbi * NW) * nb + pk) * 256 + ph * 128, lane);
             };
             auto pnext = [&]() { ph ^= 1; if (ph == 0) ++pbi; pnorm(); };
             pnorm();
@@ -1576,9 +1593,7 @@ __global__ void __launch_bounds__(512, 1) sweep_left4_kernel(SweepParamsL<T> p, 
 #pragma unroll
                             for (int i = 1; i < TPW; ++i) ob = (pi == i) ? obase[i] : ob;
                             const T* src = Lg + (long long)pk * R * 16 + ob;
-                            T* dst = ringw + stage * 128 + lane;
-#pragma unroll
-                            for (int kk = 0; kk < 4; ++kk) Num<T>::cp_async(dst + 32 * kk, src + 4 * kk);
+                            Num<T>::fifo_rows(ringw + stage * 128, src, lane);
                         };
                         pnorm();
                         int pstage = 0, cstage = 0;
@@ -1666,10 +1681,7 @@ __global__ void __launch_bounds__(512, 1) sweep_left4_kernel(SweepParamsL<T> p, 
                         int pk = nb - 1, pbi = 0, ph = 0;
                         auto pnorm = [&]() { while (pk >= 1 && (pbi >= RBW || warp + pbi * ND >= pk)) { --pk; pbi = 0; } };
                         auto issue = [&](const int stage) {
-                            const T* src = Ug + ((long long)(warp + pbi * ND) * nb + pk) * 256 + ph * 128 + lane;
-                            T* dst = ringw + stage * 128 + lane;
-#pragma unroll
-                            for (int kk = 0; kk < 4; ++kk) Num<T>::cp_async(dst + 32 * kk, src + 32 * kk);
+                            Num<T>::fifo_flat(ringw + stage * 128, Ug + ((long long)(warp + pbi * ND) * nb + pk) * 256 + ph * 128, lane);
                         };
                         auto pnext = [&]() { ph ^= 1; if (ph == 0) ++pbi; pnorm(); };
                         pnorm();
@@ -1781,11 +1793,12 @@ LeftGeom left_geom(int r, int m) {
     gm.R = (r + 15) / 16 * 16;
     gm.nb = gm.R / 16;
     // measured choice (profiles/r02_sweep_left_variants.md).  complex128: four 4-warp CTAs up to R = 112, two 8-warp CTAs up to 256, one
-    // 16-warp CTA above; float64: four 4-warp CTAs up to 128 (two blocks per warp) and up to 192 (four blocks per warp), three 8-warp
-    // CTAs up to 256, two 8-warp CTAs with four blocks per warp above
+    // 16-warp CTA above; float64: four 4-warp CTAs up to 128 (two blocks per warp) and up to 160 (four blocks per warp), three 8-warp
+    // CTAs up to 256 (at 100 points per CTA: r = 176 1.20 M against 0.97 M, r = 192 1.05 M against 0.76 M points/s), two 8-warp CTAs with
+    // four blocks per warp above
     int cfg;
     if (sizeof(T) == 16) cfg = gm.nb <= 7 ? 1 : (gm.nb <= 16 ? 2 : 3);
-    else cfg = gm.nb <= 8 ? 1 : (gm.nb <= 12 ? 5 : (gm.nb <= 16 ? 2 : 4));
+    else cfg = gm.nb <= 8 ? 1 : (gm.nb <= 10 ? 5 : (gm.nb <= 16 ? 2 : 4));
     const int cfg_auto = cfg;
     if (const char* e = getenv("MF_LEFT_CFG")) {
         const int c = atoi(e);

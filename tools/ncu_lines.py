@@ -69,6 +69,23 @@ for key, cnt in sorted(agg.items(), key=lambda kv: -kv[1]["samples"])[:top]:
     reasons = ", ".join(f"{c[6:]} {v / cnt['samples'] * 100:.0f}%" for c, v in cnt.most_common(4) if c != "samples")
     print(f"{cnt['samples'] / tot * 100:5.1f}%  inst {instr[key] / sum(instr.values()) * 100:4.1f}%  {fn}:{ln:<4} {text}\n          [{reasons}]")
 
+if os.environ.get("SHARED_CONFLICTS") and "L1 Wavefronts Shared Excessive" in ix:
+    exc, wav = collections.Counter(), collections.Counter()
+    for r in body:
+        off = int(r[ix["Address"]], 16) - base
+        key = linemap.get(off, (("?", 0), ""))[0]
+        exc[key] += float(r[ix["L1 Wavefronts Shared Excessive"]] or 0)
+        wav[key] += float(r[ix["L1 Wavefronts Shared"]] or 0)
+    te, tw = sum(exc.values()), sum(wav.values())
+    print(f"\nshared-memory wavefronts {tw:.0f}, excessive (bank conflicts) {te:.0f} = {te / max(tw, 1) * 100:.1f} %; lines with the most excessive wavefronts:")
+    for key, v in exc.most_common(12):
+        fn, ln = key
+        if fn not in srcs:
+            pth = os.path.join(os.path.dirname(os.path.abspath(lib)), "csrc", fn)
+            srcs[fn] = open(pth).read().splitlines() if os.path.exists(pth) else []
+        text = srcs[fn][ln - 1].strip()[:100] if 0 < ln <= len(srcs[fn]) else ""
+        print(f"{v / max(te, 1) * 100:5.1f}%  ({v:.0f} of {wav[key]:.0f} wavefronts)  {fn}:{ln:<4} {text}")
+
 if os.environ.get("SASS_RANGE"):
     lo, hi = (int(v) for v in os.environ["SASS_RANGE"].split("-"))
     print(f"\nSASS with most samples attributed to lines {lo}-{hi} (and inlined headers in between):")
