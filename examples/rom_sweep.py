@@ -3,26 +3,25 @@
 sweep (SuperLU on the host, as the north star prescribes), reduced-order sweep on the GPU (greedy basis, projection, batched
 solves, S-parameters), and the per-frequency difference the reference prints (`main.py:42-44`, `:67-68`).
 
-    python examples/rom_sweep.py [--data DIR] [--points 100]
+    python examples/rom_sweep.py [--data DIR] [--points 100] [--replicate K]
 
-``--data DIR`` loads ``Ct.npy``, ``Tt.npy``, ``WP.npy`` exactly like the reference (dense ``.npy`` arrays).  The reference
-ships only ``WP.npy`` (``Ct``/``Tt`` are missing large blobs), so without ``--data`` a synthetic N=3411 waveguide surrogate of
-the same size is paired with a port matrix of the shipped ``WP.npy``'s structure.  Plots are replaced by a JSON summary.
+``--data DIR`` loads ``Ct``, ``Tt``, ``WP`` like the reference (dense ``.npy`` arrays, ``main.py:21-23``) or from the sparse
+``.npz`` / header-less ``.csv`` forms (``morfem_b200.data_io``).  The reference ships only ``WP.npy`` (``Ct``/``Tt`` are
+missing large blobs), so without ``--data`` a synthetic N=3411 waveguide surrogate of the same size is paired with a port
+matrix of the shipped ``WP.npy``'s structure.  ``--replicate K`` runs K uncoupled copies of the model on the block diagonal
+(the scaling fixture of ``fake_interpolate_bigger_sample.py``).  Plots are replaced by a JSON summary.
 """
 import argparse
 import json
-import math
 import os
 import sys
 import time
 
 import numpy as np
 from numpy.linalg import norm
-from scipy.constants import pi, c as c_lightspeed
-from scipy.sparse import csc_array
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from morfem_b200 import synthetic                                                                       # noqa: E402
+from morfem_b200 import data_io, synthetic                                                              # noqa: E402
 from morfem_b200.test_helpers import finite_element_method_gsm, finite_element_method_model_order_reduction_gsm   # noqa: E402
 
 
@@ -30,21 +29,22 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--data", default=None, help="directory holding Ct.npy, Tt.npy, WP.npy (reference layout)")
     ap.add_argument("--points", type=int, default=100)
+    ap.add_argument("--replicate", type=int, default=1, help="K uncoupled copies of the model (block-diagonal operators, stacked ports)")
     args = ap.parse_args()
 
     frequency_points = np.linspace(3e9, 5e9, args.points)           # main.py:18
     gate_count = 2                                                    # main.py:19
-    if args.data and all(os.path.exists(os.path.join(args.data, f)) for f in ("Ct.npy", "Tt.npy", "WP.npy")):
-        in_c = csc_array(np.load(os.path.join(args.data, "Ct.npy")))        # main.py:21-23
-        in_gamma = csc_array(np.load(os.path.join(args.data, "Tt.npy")))
-        in_b = csc_array(np.load(os.path.join(args.data, "WP.npy")))
-        in_gamma = in_gamma * (-((2 * pi) / c_lightspeed) ** 2)           # main.py:25
-        in_b = in_b * math.sqrt(1 / (8 * 1e-7 * pi ** 2))                 # main.py:26
+    if args.data:
+        ct, tt, wp = data_io.load_operators(args.data)                  # main.py:21-23 (dense .npy), or sparse .npz / .csv
         source = args.data
     else:
         ct, tt = synthetic.waveguide_operators(9, 1, 379)               # 3411 DOFs, like the shipped WP.npy
-        in_c, in_gamma, in_b = synthetic.driver_scaled(ct, tt, synthetic.shipped_port_matrix())
+        wp = synthetic.shipped_port_matrix()
         source = "synthetic N=3411 surrogate + port matrix with the structure of the shipped data/WP.npy"
+    if args.replicate > 1:
+        ct, tt, wp = data_io.replicate_block_diagonal(ct, tt, wp, args.replicate)
+        source += f", replicated x{args.replicate} on the block diagonal"
+    in_c, in_gamma, in_b = synthetic.driver_scaled(ct, tt, wp)          # main.py:25-26
 
     t0 = time.time()
     gsm_ref = finite_element_method_gsm(frequency_points, gate_count, in_c, in_gamma, in_b)                           # main.py:28
