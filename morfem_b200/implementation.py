@@ -33,7 +33,8 @@ from typing import Callable, Optional
 
 import numpy as np
 from scipy.sparse import csc_array, issparse
-from scipy.sparse.linalg import splu
+
+from . import full_order
 
 ERROR_THRESHOLD = 1e-6
 USE_EQUALLY_DISTRIBUTED = False
@@ -42,6 +43,7 @@ PLOT_GREEDY_ITERATIONS = False             # accepted for compatibility; plottin
 USE_OPM = False                            # True: incremental greedy search (only the new columns are orthonormalised, multiplied and projected)
 TRUNCATION_TOL = 0.0
 VERBOSE = False
+FULL_ORDER_THREADS = None                  # host threads of the full-order SuperLU solves (None: every core this process may use)
 
 
 class ModelDefinition:
@@ -263,21 +265,19 @@ def _warn_singular(info_host: np.ndarray):
 def solve_fem_point(t: float, md: ModelDefinition):
     """solves (t0*A0 + t1*A1 + t2*A2)X = B for a specific point t in a domain (implementation.py:468-480)"""
     if issparse(md.a0) or issparse(md.a1) or issparse(md.a2):
-        a = system_matrix(t, md)
-        return splu(a).solve(impulse_vector(t, md))      # full-order snapshot: stays scipy/SuperLU (north star)
+        # full-order snapshot: stays scipy/SuperLU (north star); pattern, ordering and dense ports prepared once per model
+        return full_order.solver_for(md).solve(t)
     one = ModelDefinition(np.array([t], dtype=np.float64), md.a0, md.a1, md.a2, md.b, md.t_a0, md.t_a1, md.t_a2, md.t_b)
     return solve_finite_element_method(one)[0]
 
 
 def solve_finite_element_method(md: ModelDefinition):
     """implementation.py:189-194.  Dense (reduced) models run as one batched GPU sweep; sparse (full-order) models
-    keep the reference's per-point SuperLU loop."""
+    keep the reference's per-point SuperLU factorisations, with the point-independent work hoisted and the points spread
+    over the host cores (``full_order.FullOrderSolver``)."""
     domain = np.asarray(md.domain)
     if issparse(md.a0) or issparse(md.a1) or issparse(md.a2):
-        x_in_domain = np.zeros((domain.size, md.b.shape[0], md.b.shape[1]))
-        for i in range(domain.size):
-            x_in_domain[i] = solve_fem_point(domain[i], md)
-        return x_in_domain
+        return full_order.solver_for(md).solve_many(domain, threads=FULL_ORDER_THREADS)
     from . import device as dv
     real = _real_inputs(md.a0, md.a1, md.a2, md.b)        # the reference's reduced models are real: float64 sweep kernel
     up = (lambda a: dv.real_or_complex_to_device(np.asarray(a))) if real else dv.to_device_c128
@@ -309,9 +309,13 @@ def projection_base_equally_distributed(md: ModelDefinition):
     reduction_indices = np.linspace(0, md.domain.size - 1,
                                     math.floor(md.domain.size * (1 - EQUALLY_DISTRIBUTED_REDUCTION_RATE)), dtype=int)
     vector_count = md.b.shape[1]
-    q = np.empty((md.b.shape[0], vector_count * reduction_indices.size))
-    for i in range(reduction_indices.size):
-        q[:, vector_count * i:vector_count * i + vector_count] = solve_fem_point(md.domain[reduction_indices[i]], md)
+    if issparse(md.a0) or issparse(md.a1) or issparse(md.a2):
+        x = full_order.solver_for(md).solve_many(md.domain[reduction_indices], threads=FULL_ORDER_THREADS)   # (P, N, M)
+        q = np.ascontiguousarray(x.transpose(1, 0, 2).reshape(md.b.shape[0], vector_count * reduction_indices.size))
+    else:
+        q = np.empty((md.b.shape[0], vector_count * reduction_indices.size))
+        for i in range(reduction_indices.size):
+            q[:, vector_count * i:vector_count * i + vector_count] = solve_fem_point(md.domain[reduction_indices[i]], md)
     qd, _ = _orthonormal_basis_device(q, md)
     return _basis_to_host(qd, md)
 
@@ -472,7 +476,11 @@ def projection_base(md: ModelDefinition, _return_device: bool = False, _ops: Opt
     re-orthonormalising ``[q | q_new]`` each time (:297-298)."""
     from . import device as dv
     ops = _ops or _DeviceOperators(md)            # a caller that projects afterwards passes its own (one upload per call)
-    initial_vectors = np.hstack((solve_fem_point(md.domain[0], md), solve_fem_point(md.domain[-1], md)))
+    if issparse(md.a0) or issparse(md.a1) or issparse(md.a2):   # the two end points, factorised side by side
+        ends = full_order.solver_for(md).solve_many(md.domain[[0, -1]], threads=FULL_ORDER_THREADS)
+        initial_vectors = np.hstack((ends[0], ends[1]))
+    else:
+        initial_vectors = np.hstack((solve_fem_point(md.domain[0], md), solve_fem_point(md.domain[-1], md)))
     if USE_OPM:                                   # incremental search: implementation.py:230-263 (set-up), :275-295 (growth)
         state = _GreedyState(md, ops, initial_vectors)
         projection_base.last_errors = []
