@@ -1832,12 +1832,24 @@ int left_occupancy(K kern, int threads, const LeftGeom& gm, int* per_sm) {
     return 0;
 }
 
-// Measured on B200 (profiles/r02_sweep_left_variants.md): the look-ahead body wins for complex128 up to R = 192 (+20..40 %) and
-// above R = 256 (+2 %); at R = 208..256 the plain body is ~5 % ahead; float64 (a quarter of the DMMA work, all latency): plain body.
+// Measured on B200 (profiles/r02_sweep_left_variants.md): complex128 runs the look-ahead body at every size -- at R = 208..256 it
+// only wins while the two CTAs of an SM stay in step, i.e. together with short launches (left_chunk below; in one long launch the plain
+// body is ~5..15 % ahead there); float64 (a quarter of the DMMA work, all latency): plain body.
 template <typename T>
 int left_version(const LeftGeom& gm) {
-    if (sizeof(T) == 16) return (gm.R <= 192 || gm.R > 256) ? 3 : 2;
-    return 2;
+    (void)gm;
+    return sizeof(T) == 16 ? 3 : 2;
+}
+
+// Points per CTA and launch (0 = the whole batch in one launch); see launch_left.  Measured (profiles/r02_sweep_left_chunks.md, launches of
+// 100..150 points per CTA, points/s single launch -> 2 points per CTA and launch): complex128 look-ahead body R = 208 3.9e5 (plain body) ->
+// 4.9e5, 224 3.4e5 -> 4.1e5, 240 3.0e5 -> 3.55e5, 256 2.7e5 -> 3.06e5; no change at R <= 192 and R >= 320 (one CTA per SM there);
+// float64 plain body R = 192 1.05e6 -> 1.16e6, 224 7.3e5 -> 8.0e5, 256 5.7e5 -> 6.1e5, 512 9.1e4 -> 9.4e4; no gain at R = 160.
+template <typename T>
+long long left_chunk(const LeftGeom& gm, int ver) {
+    (void)ver;                                                       // both bodies gain at these sizes (plain body at R = 256: 2.7e5 -> 2.9e5)
+    if (sizeof(T) == 16) return (gm.R > 192 && gm.R <= 256) ? 2 : 0;
+    return gm.R >= 192 ? 2 : 0;
 }
 
 template <typename T, int NW, int RBW, int MINB>
@@ -1862,8 +1874,28 @@ int launch_left(SweepParamsL<T> p, const LeftGeom& gm, size_t ws_bytes, cudaStre
     p.remap = env_remap >= 0 ? (env_remap != 0) : (NW == 8 && gm.R <= 128);
     static const bool want_timing = getenv("MF_LEFT_TIMING") != nullptr;     // debugging aid: blocks, prints the phase clocks of CTA 0
     if (want_timing) { MF_CHECK_CUDA(cudaMalloc(&p.timing, 16 * sizeof(unsigned long long))); MF_CHECK_CUDA(cudaMemsetAsync(p.timing, 0, 16 * 8, stream)); }
-    kern<<<(unsigned)grid, NW * 32, gm.smem, stream>>>(p, gm.R);
-    MF_CHECK_LAUNCH();
+    // Points per CTA and launch.  The CTAs of an SM start a launch in step (both in their panel, then both in the DMMA phase) and drift
+    // apart within ~20 points, after which one CTA's scalar-FP64 panel runs against the other's DMMA stream; cutting the
+    // batch into short launches keeps them in step.  0 = one launch for the whole batch.
+    long long chunk = left_chunk<T>(gm, ver);
+    if (const char* e = getenv("MF_LEFT_CHUNK")) chunk = atoll(e);
+    if (want_timing || chunk <= 0 || chunk * grid >= p.F) {
+        kern<<<(unsigned)grid, NW * 32, gm.smem, stream>>>(p, gm.R);
+        MF_CHECK_LAUNCH();
+    } else {
+        const long long per_launch = chunk * grid;
+        for (long long f0 = 0; f0 < p.F; f0 += per_launch) {
+            SweepParamsL<T> q = p;
+            q.F = p.F - f0 < per_launch ? p.F - f0 : per_launch;
+            q.c0 = p.c0 + f0; q.c1 = p.c1 + f0; q.c2 = p.c2 + f0; q.cb = p.cb + f0;
+            if (p.zs) q.zs = p.zs + f0;
+            if (p.X) q.X = p.X + f0 * (long long)p.r * p.m;
+            if (p.S) q.S = p.S + f0 * (long long)p.m * p.m;
+            if (p.info) q.info = p.info + f0;
+            kern<<<(unsigned)(q.F < grid ? q.F : grid), NW * 32, gm.smem, stream>>>(q, gm.R);
+            MF_CHECK_LAUNCH();
+        }
+    }
     if (want_timing) {
         unsigned long long h[16];
         MF_CHECK_CUDA(cudaMemcpyAsync(h, p.timing, sizeof(h), cudaMemcpyDeviceToHost, stream));

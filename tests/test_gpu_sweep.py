@@ -336,3 +336,63 @@ def test_public_stage3_and_stage4_api_match_live_reference(dv):
     xc = impl.solve_finite_element_method(mdc)
     xr = orc.reduced_sweep(f[:5], a0c, g["a1"], g["a2"], g["b"], lambda t: 1.0, lambda t: t, lambda t: t ** 2, orc.b_coefficient, complex_ok=True)
     assert np.iscomplexobj(xc) and np.all(per_point_rel(xc, xr) < 1e-8)
+
+
+@pytest.mark.parametrize("r,m,real", [(208, 3, False), (256, 4, False), (224, 2, True), (200, 5, True)])
+def test_left_looking_bodies_and_chunked_launches(dv, r, m, real, monkeypatch):
+    """The left-looking kernel cuts a long batch into launches of a few points per CTA (``left_chunk``; MF_LEFT_CHUNK overrides) and
+    has two bodies (MF_LEFT_VER: 2 plain, 3 look-ahead).  A batch that spans several launches with a ragged last one: the same body
+    gives the same bits whatever the launch length (x, S and info land at the right points), both bodies and the library's own choice
+    match the oracle, and a singular system at one point deep inside the batch is reported at that point only."""
+    from scipy.constants import pi, epsilon_0
+    from morfem_b200 import synthetic
+    nf = 700                                           # 296 resident CTAs: launches of 296 + 296 + 108 points at one point per CTA
+    a0, a1, a2, b = synthetic.reduced_model(r, m, seed=500 + r)
+    f = np.linspace(3e9, 5e9, nf)
+    tb = orc.b_coefficient
+    cb = np.array([tb(t) for t in f])
+    dev = dv.require_cuda()
+    up = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(dev)  # noqa: E731
+    conv = up if real else dv.to_device_c128
+    ops = (dv.symmetrize(conv(a0)), None, dv.symmetrize(conv(a2)), conv(b))
+    coef = (up(np.ones_like(f)), up(f), up(f ** 2), up(cb), up(2 * pi * f * epsilon_0))
+
+    def go(ver=None, chunk=None, operands=ops, coefficients=coef, want_gsm=True):
+        for key, val in (("MF_LEFT_VER", ver), ("MF_LEFT_CHUNK", chunk)):
+            if val is None:
+                monkeypatch.delenv(key, raising=False)
+            else:
+                monkeypatch.setenv(key, str(val))
+        res = dv.sweep(*operands, *coefficients, want_x=True, want_gsm=want_gsm, variant=5)
+        torch.cuda.synchronize()
+        return res
+
+    sample = np.array([0, 1, 147, 295, 296, 297, 591, 592, 593, 650, 698, 699])
+    x_ref = orc.reduced_sweep(f[sample], a0, a1, a2, b, lambda t: 1.0, lambda t: t, lambda t: t ** 2, tb)
+    s_ref = orc.scattering_sweep(f[sample], x_ref, b)
+    cond = np.array([np.linalg.cond(orc.system_matrix(1.0, t, t ** 2, a0, a1, a2)) for t in f[sample]])
+    tol = np.maximum(1e-10, 20 * EPS * cond)
+    for ver in (2, 3):
+        one = go(ver, 0)
+        assert not np.any(one.info.cpu().numpy())
+        for chunk in (1, 2):
+            cut = go(ver, chunk)
+            assert torch.equal(cut.x, one.x) and torch.equal(cut.gsm, one.gsm) and torch.equal(cut.info, one.info), (ver, chunk)
+        assert np.all(per_point_rel(one.x.cpu().numpy()[sample].real, x_ref) < tol), ver
+        assert np.all(per_point_rel(one.gsm.cpu().numpy()[sample], s_ref) < tol), ver
+    own = go()                                         # the library's choice of body and launch length
+    assert np.all(per_point_rel(own.x.cpu().numpy()[sample].real, x_ref) < tol)
+    assert np.all(per_point_rel(own.gsm.cpu().numpy()[sample], s_ref) < tol)
+    # A(t) = I - c2(t) E with E = e_k e_k^T and c2 = 1 at point 600 only: exactly singular there (LAPACK info k + 1), identity elsewhere
+    k = r // 2 + 5
+    e = np.zeros((r, r))
+    e[k, k] = -1.0
+    c2 = np.zeros(nf)
+    c2[600] = 1.0
+    sing_ops = (conv(np.eye(r)), None, conv(e), conv(np.ones((r, m))))
+    sing_coef = (up(np.ones(nf)), up(np.zeros(nf)), up(c2), up(np.ones(nf)), up(np.ones(nf)))
+    for ver, chunk in ((2, 1), (3, 2), (None, None)):
+        res = go(ver, chunk, sing_ops, sing_coef, want_gsm=False)
+        info = res.info.cpu().numpy()
+        assert info[600] == k + 1 and not np.any(np.delete(info, 600)), (ver, chunk)
+        assert np.all(res.x.cpu().numpy()[:600].real == 1.0)
