@@ -1992,10 +1992,11 @@ size_t left_ws_bytes(int r, int m, long long F) {
 
 }  // namespace
 
+// The Makefile compiles this file twice, once per element type (MF_LEFT_PART = 1: complex128, 2: float64), so that the two halves of the
+// instantiations build side by side; without the macro one translation unit holds both.
+#if !defined(MF_LEFT_PART) || MF_LEFT_PART == 1
 bool sweep_left_supports_c128(int r, int m) { return left_supports<cplx>(r, m); }
-bool sweep_left_supports_f64(int r, int m) { return left_supports<double>(r, m); }
 size_t sweep_left_ws_bytes_c128(int r, int m, long long F) { return left_ws_bytes<cplx>(r, m, F); }
-size_t sweep_left_ws_bytes_f64(int r, int m, long long F) { return left_ws_bytes<double>(r, m, F); }
 
 int sweep_left_launch_c128(const SweepParams& q, size_t ws_bytes, cudaStream_t stream) {
     SweepParamsL<cplx> p;
@@ -2004,6 +2005,11 @@ int sweep_left_launch_c128(const SweepParams& q, size_t ws_bytes, cudaStream_t s
     p.ws = q.ws; p.ws_stride = 0; p.timing = nullptr;
     return dispatch_left<cplx>(p, ws_bytes, stream);
 }
+#endif
+
+#if !defined(MF_LEFT_PART) || MF_LEFT_PART == 2
+bool sweep_left_supports_f64(int r, int m) { return left_supports<double>(r, m); }
+size_t sweep_left_ws_bytes_f64(int r, int m, long long F) { return left_ws_bytes<double>(r, m, F); }
 
 int sweep_left_launch_f64(const double* A0, const double* A1, const double* A2, long long lda, const double* Br, long long ldb, int r, int m,
                           const double* c0, const double* c1, const double* c2, const double* cb, const double* zs, long long F,
@@ -2014,3 +2020,4 @@ int sweep_left_launch_f64(const double* A0, const double* A1, const double* A2, 
     p.ws = (double*)ws; p.ws_stride = 0; p.timing = nullptr;
     return dispatch_left<double>(p, ws_bytes, stream);
 }
+#endif
