@@ -10,6 +10,6 @@ tail -c 1200 gpurun_out/bench_cfg3_n1.log; tail -3 gpurun_out/bench_cfg3_n1.err
 timeout 600 python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/bench_reference_cfg3.log 2>&1; echo "reference rc=$?"
 tail -c 600 gpurun_out/bench_reference_cfg3.log
 timeout 600 python bench.py --steps 2 --warmup 3 --no-parity --no-secondary --no-alt-dtype > gpurun_out/plain_bench.log 2>&1 && \
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_cfg3.csv \
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/launches_cfg3.csv \
     python bench.py --steps 2 --warmup 3 --no-parity --no-secondary --no-alt-dtype > gpurun_out/ncu_bench.log 2>&1
 echo "ncu launch list rc=$?"; tail -2 gpurun_out/launches_cfg3.csv
