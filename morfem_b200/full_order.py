@@ -48,8 +48,8 @@ class FullOrderSolver:
 
     def __init__(self, md, reuse_ordering: bool = True):
         self.md = md
-        ops = [_symmetrised_csc(a) for a in (md.a0, md.a1, md.a2)]
-        n = ops[0].shape[0]
+        n = next(a.shape[0] for a in (md.a0, md.a1, md.a2) if a is not None)
+        ops = [_symmetrised_csc(csc_matrix((n, n)) if a is None else a) for a in (md.a0, md.a1, md.a2)]   # None = zero operator
         # union pattern: explicit ones on every stored position (an operator value that happens to be 0.0 keeps its slot)
         pat = None
         for s in ops:
@@ -157,6 +157,8 @@ _solvers = {}      # one prepared solver per model, a few entries at most
 
 def _fingerprint(a):
     """Cheap content check of one operator (the cache is keyed by object identity; an operator edited in place must miss)."""
+    if a is None:
+        return None
     data = a.data if issparse(a) else np.asarray(a)
     return (a.shape, int(getattr(a, "nnz", data.size)), complex(data.sum()) if data.size else 0j)
 

@@ -88,6 +88,9 @@ def test_public_entry_points_use_the_prepared_solver():
 
 def test_empty_domain_and_single_point():
     md = _model(points=3)
+    ref0 = _oracle(md)[0]
     s = full_order.FullOrderSolver(md)
     assert s.solve_many(np.zeros(0)).shape == (0, s.n, 2)
-    assert np.array_equal(s.solve_many(md.domain[:1])[0], _oracle(md)[0])
+    assert np.array_equal(s.solve_many(md.domain[:1])[0], ref0)
+    md.a1 = None                                                   # "no damping term" spelled as None instead of an empty matrix
+    assert np.array_equal(full_order.solver_for(md).solve(md.domain[0]), ref0)
